@@ -121,11 +121,6 @@ def init_weights(specs, seed=0, randomize_bn=True, head_bias=None, dtype=np.floa
 
 
 # ------------------------------------------------------------------ torch forward
-def _t(a, dtype):
-    import torch
-    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
-
-
 class _Cursor:
     def __init__(self, weights):
         self.w = weights
@@ -137,32 +132,53 @@ class _Cursor:
         return out
 
 
+class _Prepared:
+    """Weights converted once to torch tensors in the layout torch wants (what a
+    keras.Model holds resident between predict calls)."""
+
+    def __init__(self, weights, dt):
+        import torch
+        self.dt = dt
+        self.t = []
+        for w in weights:
+            w = np.asarray(w)
+            t = torch.from_numpy(np.ascontiguousarray(w)).to(dt)
+            if w.ndim == 4:  # HWIO conv kernel / (kh,kw,out,in) transposed-conv kernel -> torch layout
+                t = t.permute(3, 2, 0, 1).contiguous()
+            self.t.append(t)
+
+
+def prepare(weights, precision='fp32'):
+    import torch
+    return _Prepared(weights, torch.float32 if precision == 'fp32' else torch.float64)
+
+
 def forward(x_nhwc, weights, variant='A', filters=DEFAULT_FILTERS, head='sigmoid',
             threshold=0.5, precision='fp32', return_logits=False, num_threads=None):
-    """Forward pass.  ``x_nhwc`` (N,H,W,C) float; returns ``(probs, classes)``:
-    probs (N,H,W,k) float32, classes int32 -- (N,H,W,1) for the sigmoid head
-    (``model_tools.py:445``), (N,H,W) for softmax/argmax (``:406``).
+    """Forward pass.  ``x_nhwc`` (N,H,W,C) float; ``weights`` is the keras-ordered list (or the result
+    of :func:`prepare`).  Returns ``(probs, classes)``: probs (N,H,W,k) float32, classes int32 --
+    (N,H,W,1) for the sigmoid head (``model_tools.py:445``), (N,H,W) for softmax/argmax (``:406``).
     """
     import torch
     import torch.nn.functional as F
     if num_threads:
         torch.set_num_threads(num_threads)
-    dt = torch.float32 if precision == 'fp32' else torch.float64
+    prep = weights if isinstance(weights, _Prepared) else prepare(weights, precision)
+    dt = prep.dt
     nconv = 2 if variant == 'A' else 1
-    cur = _Cursor(weights)
+    cur = _Cursor(prep.t)
+
+    def bn(y, g, be, mu, var):
+        g, be, mu, var = (v.view(1, -1, 1, 1) for v in (g, be, mu, var))
+        return g * (y - mu) / torch.sqrt(var + BN_EPS) + be
 
     def conv_bn_relu(x):
         k, b = cur.take(2)
-        g, be, mu, var = cur.take(4)
-        y = F.conv2d(x, _t(k, dt).permute(3, 2, 0, 1), _t(b, dt), padding=k.shape[0] // 2)
-        return torch.relu(bn(y, g, be, mu, var))
-
-    def bn(y, g, be, mu, var):
-        g, be, mu, var = (_t(v, dt).view(1, -1, 1, 1) for v in (g, be, mu, var))
-        return g * (y - mu) / torch.sqrt(var + BN_EPS) + be
+        y = F.conv2d(x, k, b, padding=k.shape[-1] // 2)
+        return torch.relu(bn(y, *cur.take(4)))
 
     with torch.no_grad():
-        x = _t(np.asarray(x_nhwc), dt).permute(0, 3, 1, 2)
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x_nhwc))).to(dt).permute(0, 3, 1, 2)
         skips = []
         for _ in filters:
             for _ in range(nconv):
@@ -173,14 +189,14 @@ def forward(x_nhwc, weights, variant='A', filters=DEFAULT_FILTERS, head='sigmoid
             x = conv_bn_relu(x)
         for i in range(len(filters) - 1, -1, -1):
             k, b = cur.take(2)
-            up = F.conv_transpose2d(x, _t(k, dt).permute(3, 2, 0, 1), _t(b, dt), stride=2)
+            up = F.conv_transpose2d(x, k, b, stride=2)
             x = torch.cat([skips[i], up], dim=1)
             x = torch.relu(bn(x, *cur.take(4)))
             x = conv_bn_relu(x)
             x = conv_bn_relu(x)
         k, b = cur.take(2)
-        logits = F.conv2d(x, _t(k, dt).permute(3, 2, 0, 1), _t(b, dt))
-        assert cur.i == len(weights), 'weight list length does not match the architecture'
+        logits = F.conv2d(x, k, b)
+        assert cur.i == len(prep.t), 'weight list length does not match the architecture'
         logits = logits.permute(0, 2, 3, 1).contiguous()
         if head == 'sigmoid':
             probs = torch.sigmoid(logits)
@@ -196,8 +212,10 @@ def forward(x_nhwc, weights, variant='A', filters=DEFAULT_FILTERS, head='sigmoid
 def make_predict_fn(weights, **kw):
     """A ``keras.Model.predict`` stand-in for ``oracle.tiling`` functions:
     batch (N,h,w,C) -> probs (N,h,w,k)."""
+    prep = prepare(weights, kw.pop('precision', 'fp32'))
+
     def predict(batch, verbose=0, steps=None):
-        return forward(np.asarray(batch, dtype=np.float32), weights, **kw)[0]
+        return forward(np.asarray(batch, dtype=np.float32), prep, **kw)[0]
     return predict
 
 

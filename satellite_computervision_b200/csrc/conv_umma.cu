@@ -1,0 +1,79 @@
+// Instantiations + dispatch of the UMMA implicit-GEMM convolution kernel.
+#include "conv_umma.cuh"
+
+namespace scv {
+
+namespace {
+template <int KC, int BN, int EPI>
+cudaError_t launch_one(const ConvLaunch& L, cudaStream_t stream) {
+  conv_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  return cudaGetLastError();
+}
+template <int KC, int BN, int EPI>
+cudaError_t attr_one() {
+  return cudaFuncSetAttribute(conv_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+template <int KC, int BN>
+cudaError_t launch_epi(const ConvLaunch& L, cudaStream_t s) {
+  switch (L.EPI) {
+    case EPI_STORE: return launch_one<KC, BN, EPI_STORE>(L, s);
+    case EPI_POOL_SKIP: return launch_one<KC, BN, EPI_POOL_SKIP>(L, s);
+    case EPI_CONVT: return launch_one<KC, BN, EPI_CONVT>(L, s);
+    case EPI_HEAD:
+      if constexpr (BN <= 128) return launch_one<KC, BN, EPI_HEAD>(L, s);
+      return cudaErrorInvalidValue;
+  }
+  return cudaErrorInvalidValue;
+}
+template <int KC>
+cudaError_t launch_bn(const ConvLaunch& L, cudaStream_t s) {
+  switch (L.BN) {
+    case 32: return launch_epi<KC, 32>(L, s);
+    case 64: return launch_epi<KC, 64>(L, s);
+    case 128: return launch_epi<KC, 128>(L, s);
+    case 256: return launch_epi<KC, 256>(L, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int KC, int BN>
+cudaError_t attr_epi() {
+  cudaError_t e;
+  if ((e = attr_one<KC, BN, EPI_STORE>()) != cudaSuccess) return e;
+  if ((e = attr_one<KC, BN, EPI_POOL_SKIP>()) != cudaSuccess) return e;
+  if ((e = attr_one<KC, BN, EPI_CONVT>()) != cudaSuccess) return e;
+  if constexpr (BN <= 128) {
+    if ((e = attr_one<KC, BN, EPI_HEAD>()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+template <int KC>
+cudaError_t attr_bn() {
+  cudaError_t e;
+  if ((e = attr_epi<KC, 32>()) != cudaSuccess) return e;
+  if ((e = attr_epi<KC, 64>()) != cudaSuccess) return e;
+  if ((e = attr_epi<KC, 128>()) != cudaSuccess) return e;
+  if ((e = attr_epi<KC, 256>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
+  switch (L.KC) {
+    case 16: return launch_bn<16>(L, stream);
+    case 32: return launch_bn<32>(L, stream);
+    case 64: return launch_bn<64>(L, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t conv_init_attributes() {
+  cudaError_t e;
+  if ((e = attr_bn<16>()) != cudaSuccess) return e;
+  if ((e = attr_bn<32>()) != cudaSuccess) return e;
+  if ((e = attr_bn<64>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+}  // namespace scv

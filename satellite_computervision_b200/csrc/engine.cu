@@ -1,0 +1,1533 @@
+// libscv.so -- engine + C-ABI of the B200-native tiled U-Net predict path.
+// See include/scv.h for the boundary and the reference call sites it replaces.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/scv.h"
+#include "conv_umma.cuh"
+#include "tile_kernels.cuh"
+
+using namespace scv;
+
+// ============================================================== error handling
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(SCV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define SCV_TRY(expr)       \
+  do {                      \
+    int _r = (expr);        \
+    if (_r != SCV_OK) return _r; \
+  } while (0)
+
+// ============================================================== tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// bf16 NHWC activation tensor (N,H,W,Cpitch) viewed as 4-D (C, W, H, N); box (KC, TW, TH, TN).
+static int make_act_tmap(CUtensorMap* tm, const void* ptr, int N, int H, int W, int Cpitch, int KC, int TW, int TH,
+                         int TN) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)Cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Cpitch * 2, (cuuint64_t)W * Cpitch * 2, (cuuint64_t)H * W * Cpitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled(act N=%d H=%d W=%d C=%d box=%d,%d,%d,%d) -> %d", N, H, W, Cpitch,
+                KC, TW, TH, TN, (int)r);
+  return SCV_OK;
+}
+
+// bf16 weights [Ntotal][Ktotal] (K contiguous) viewed as 2-D (K, N); box (KC, BN).
+static int make_w_tmap(CUtensorMap* tm, const void* ptr, int Ktotal, int Ntotal, int KC, int BN) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktotal, (cuuint64_t)Ntotal};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktotal * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled(weights K=%d N=%d box=%d,%d) -> %d", Ktotal, Ntotal, KC, BN,
+                (int)r);
+  return SCV_OK;
+}
+
+// ============================================================== architecture
+static int pad_channels(int c) {
+  if (c <= 16) return 16;
+  if (c <= 32) return 32;
+  return (c + 63) / 64 * 64;
+}
+static int kc_for(int cpad) { return cpad <= 16 ? 16 : (cpad <= 32 ? 32 : 64); }
+static int bn_for(int ntotal) {
+  for (int bn : {256, 128, 64, 32})
+    if (ntotal % bn == 0) return bn;
+  return 0;
+}
+static void tile_box(int W, int* TW, int* TH, int* TN) {
+  if (W % 16 == 0) {
+    *TW = 16, *TH = 8, *TN = 1;
+  } else if (W % 8 == 0 || W > 12) {
+    *TW = 8, *TH = 8, *TN = 2;
+  } else {
+    *TW = 4, *TH = 4, *TN = 8;
+  }
+}
+
+struct WeightSpec {
+  std::string name;
+  int ndim;
+  int64_t shape[4];
+};
+
+static int validate_config(const scv_config* c) {
+  if (!c) return fail(SCV_ERR_INVALID, "config is NULL");
+  if (c->nlevels < 1 || c->nlevels > SCV_MAX_LEVELS) return fail(SCV_ERR_INVALID, "nlevels %d out of range", c->nlevels);
+  if (c->nchannels < 1 || c->nchannels > SCV_MAX_BANDS)
+    return fail(SCV_ERR_INVALID, "nchannels %d out of range [1,%d]", c->nchannels, SCV_MAX_BANDS);
+  if (c->nclasses < 1 || c->nclasses > SCV_MAX_CLASSES)
+    return fail(SCV_ERR_INVALID, "nclasses %d out of range [1,%d]", c->nclasses, SCV_MAX_CLASSES);
+  if (c->head == SCV_HEAD_SIGMOID && c->nclasses != 1) return fail(SCV_ERR_INVALID, "sigmoid head needs nclasses == 1");
+  if (c->head != SCV_HEAD_SIGMOID && c->head != SCV_HEAD_SOFTMAX) return fail(SCV_ERR_INVALID, "unknown head %d", c->head);
+  for (int i = 0; i < c->nlevels; ++i) {
+    const int f = c->filters[i];
+    if (f < 32 || f % 32 != 0 || (f > 32 && f % 64 != 0))
+      return fail(SCV_ERR_INVALID, "filters[%d]=%d unsupported: must be 32 or a multiple of 64", i, f);
+  }
+  if (c->filters[0] > 128) return fail(SCV_ERR_INVALID, "filters[0]=%d > 128 unsupported by the fused head", c->filters[0]);
+  return SCV_OK;
+}
+
+// keras model.get_weights() order (see oracle/unet.py weight_specs for the same walk)
+static void build_specs(const scv_config* c, std::vector<WeightSpec>* out) {
+  auto add = [&](const std::string& n, std::initializer_list<int64_t> s) {
+    WeightSpec w;
+    w.name = n;
+    w.ndim = (int)s.size();
+    int i = 0;
+    for (auto v : s) w.shape[i++] = v;
+    for (; i < 4; ++i) w.shape[i] = 1;
+    out->push_back(w);
+  };
+  auto conv = [&](const std::string& n, int cin, int cout, int k) {
+    add(n + "/kernel", {k, k, cin, cout});
+    add(n + "/bias", {cout});
+  };
+  auto bn = [&](const std::string& n, int ch) {
+    add(n + "/gamma", {ch});
+    add(n + "/beta", {ch});
+    add(n + "/moving_mean", {ch});
+    add(n + "/moving_variance", {ch});
+  };
+  const int nconv = c->double_conv ? 2 : 1;
+  int cin = c->nchannels;
+  for (int i = 0; i < c->nlevels; ++i) {
+    for (int j = 0; j < nconv; ++j) {
+      const std::string b = "encoder_" + std::to_string(i);
+      conv(b + "/conv" + std::to_string(j), cin, c->filters[i], 3);
+      bn(b + "/bn" + std::to_string(j), c->filters[i]);
+      cin = c->filters[i];
+    }
+  }
+  const int fc = c->filters[c->nlevels - 1] * 2;
+  for (int j = 0; j < nconv; ++j) {
+    conv("center/conv" + std::to_string(j), cin, fc, 3);
+    bn("center/bn" + std::to_string(j), fc);
+    cin = fc;
+  }
+  for (int i = c->nlevels - 1; i >= 0; --i) {
+    const int f = c->filters[i];
+    const std::string b = "decoder_" + std::to_string(i);
+    add(b + "/up/kernel", {2, 2, f, cin});
+    add(b + "/up/bias", {f});
+    bn(b + "/bn_cat", 2 * f);
+    conv(b + "/conv0", 2 * f, f, 3);
+    bn(b + "/bn0", f);
+    conv(b + "/conv1", f, f, 3);
+    bn(b + "/bn1", f);
+    cin = f;
+  }
+  conv("head", cin, c->nclasses, 1);
+}
+
+// ---- layer graph -----------------------------------------------------------
+enum { L_CONV3 = 0, L_CONVT = 1 };
+
+struct BufDef {
+  int level;     // resolution = tile >> level
+  int channels;  // channel pitch
+  bool f32;      // logits
+  std::string name;
+};
+
+struct LayerDef {
+  std::string name;
+  int kind, epi;
+  int level;            // input resolution level
+  int cin_real, cin_pad;  // input channels consumed (pitch of in_buf == cin_pad)
+  int cout;             // conv: output channels; convT: F (Ntotal = 4F)
+  int ntotal;
+  int KC, BN;
+  int in_buf, out_buf, out_choff, pool_buf;
+  // keras weight-list indices (-1 = none)
+  int w_kernel, w_bias, w_bn;  // bn: index of gamma (gamma,beta,mean,var consecutive)
+  int w_skip_bn;               // EPI_POOL_SKIP: decoder bn_cat gamma index (first F channels)
+  int w_up_bn;                 // L_CONVT: decoder bn_cat gamma index (channels [F,2F))
+  double flops_per_tile_at_unit;  // FLOPs per input pixel of this layer (multiply by h*w of its level)
+  // device weights
+  __nv_bfloat16* d_w = nullptr;
+  float* d_bias = nullptr;
+  float* d_skip_s = nullptr;
+  float* d_skip_t = nullptr;
+  CUtensorMap tmB;
+};
+
+struct Arch {
+  scv_config cfg;
+  std::vector<WeightSpec> specs;
+  std::map<std::string, int> spec_index;
+  std::vector<BufDef> bufs;
+  std::vector<LayerDef> layers;
+  int x0_buf, logits_buf;
+  int c0pad;
+};
+
+static int build_arch(const scv_config* c, Arch* a) {
+  SCV_TRY(validate_config(c));
+  a->cfg = *c;
+  build_specs(c, &a->specs);
+  for (size_t i = 0; i < a->specs.size(); ++i) a->spec_index[a->specs[i].name] = (int)i;
+  auto idx = [&](const std::string& n) { return a->spec_index.at(n); };
+  auto add_buf = [&](int level, int ch, bool f32, const std::string& n) {
+    a->bufs.push_back({level, ch, f32, n});
+    return (int)a->bufs.size() - 1;
+  };
+  const int L = c->nlevels;
+  const int nconv = c->double_conv ? 2 : 1;
+  a->c0pad = pad_channels(c->nchannels);
+  a->x0_buf = add_buf(0, a->c0pad, false, "x0");
+  std::vector<int> t(L, -1), cat(L), pooled(L);
+  for (int i = 0; i < L; ++i) {
+    t[i] = add_buf(i, c->filters[i], false, "t" + std::to_string(i));  // enc conv0 out (variant A) / dec conv0 out
+    cat[i] = add_buf(i, 2 * c->filters[i], false, "cat" + std::to_string(i));
+    pooled[i] = add_buf(i + 1, c->filters[i], false, "pool" + std::to_string(i));
+  }
+  const int fc = c->filters[L - 1] * 2;
+  const int ct1 = nconv == 2 ? add_buf(L, fc, false, "center0") : -1;
+  const int ct2 = add_buf(L, fc, false, "center1");
+  std::vector<int> d2(L, -1);
+  for (int i = 1; i < L; ++i) d2[i] = add_buf(i, c->filters[i], false, "dec" + std::to_string(i));
+  a->logits_buf = add_buf(0, c->nclasses, true, "logits");
+
+  auto conv_layer = [&](const std::string& name, int level, int cin_real, int in_buf, int cout) {
+    LayerDef l{};
+    l.name = name;
+    l.kind = L_CONV3;
+    l.epi = EPI_STORE;
+    l.level = level;
+    l.cin_real = cin_real;
+    l.cin_pad = a->bufs[in_buf].channels;
+    l.cout = cout;
+    l.ntotal = cout;
+    l.KC = kc_for(l.cin_pad);
+    l.BN = bn_for(cout);
+    l.in_buf = in_buf;
+    l.out_buf = -1;
+    l.out_choff = 0;
+    l.pool_buf = -1;
+    l.w_kernel = idx(name + "/kernel");
+    l.w_bias = idx(name + "/bias");
+    l.w_bn = -1;
+    l.w_skip_bn = l.w_up_bn = -1;
+    l.flops_per_tile_at_unit = 2.0 * cin_real * cout * 9;
+    return l;
+  };
+
+  int cur = a->x0_buf, cur_real = c->nchannels;
+  for (int i = 0; i < L; ++i) {
+    const std::string b = "encoder_" + std::to_string(i);
+    for (int j = 0; j < nconv; ++j) {
+      LayerDef l = conv_layer(b + "/conv" + std::to_string(j), i, cur_real, cur, c->filters[i]);
+      l.w_bn = idx(b + "/bn" + std::to_string(j) + "/gamma");
+      if (j == nconv - 1) {
+        l.epi = EPI_POOL_SKIP;
+        l.out_buf = cat[i];
+        l.out_choff = 0;
+        l.pool_buf = pooled[i];
+        l.w_skip_bn = idx("decoder_" + std::to_string(i) + "/bn_cat/gamma");
+      } else {
+        l.out_buf = t[i];
+      }
+      a->layers.push_back(l);
+      cur = (j == nconv - 1) ? pooled[i] : t[i];
+      cur_real = c->filters[i];
+    }
+  }
+  for (int j = 0; j < nconv; ++j) {
+    LayerDef l = conv_layer("center/conv" + std::to_string(j), L, cur_real, cur, fc);
+    l.w_bn = idx("center/bn" + std::to_string(j) + "/gamma");
+    l.out_buf = (j == nconv - 1) ? ct2 : ct1;
+    a->layers.push_back(l);
+    cur = l.out_buf;
+    cur_real = fc;
+  }
+  for (int i = L - 1; i >= 0; --i) {
+    const int f = c->filters[i];
+    const std::string b = "decoder_" + std::to_string(i);
+    LayerDef u{};
+    u.name = b + "/up";
+    u.kind = L_CONVT;
+    u.epi = EPI_CONVT;
+    u.level = i + 1;
+    u.cin_real = cur_real;
+    u.cin_pad = a->bufs[cur].channels;
+    u.cout = f;
+    u.ntotal = 4 * f;
+    u.KC = kc_for(u.cin_pad);
+    u.BN = bn_for(u.ntotal);
+    u.in_buf = cur;
+    u.out_buf = cat[i];
+    u.out_choff = f;
+    u.pool_buf = -1;
+    u.w_kernel = idx(b + "/up/kernel");
+    u.w_bias = idx(b + "/up/bias");
+    u.w_bn = -1;
+    u.w_skip_bn = -1;
+    u.w_up_bn = idx(b + "/bn_cat/gamma");
+    u.flops_per_tile_at_unit = 2.0 * cur_real * f * 4;
+    a->layers.push_back(u);
+
+    LayerDef c0 = conv_layer(b + "/conv0", i, 2 * f, cat[i], f);
+    c0.w_bn = idx(b + "/bn0/gamma");
+    c0.out_buf = t[i];
+    a->layers.push_back(c0);
+
+    LayerDef c1 = conv_layer(b + "/conv1", i, f, t[i], f);
+    c1.w_bn = idx(b + "/bn1/gamma");
+    if (i == 0) {
+      c1.epi = EPI_HEAD;
+      c1.out_buf = a->logits_buf;
+      c1.flops_per_tile_at_unit += 2.0 * f * c->nclasses;  // fused 1x1 head
+    } else {
+      c1.out_buf = d2[i];
+    }
+    a->layers.push_back(c1);
+    cur = c1.out_buf;
+    cur_real = f;
+  }
+  for (auto& l : a->layers) {
+    if (l.BN == 0) return fail(SCV_ERR_INVALID, "layer %s: N=%d has no supported tile width", l.name.c_str(), l.ntotal);
+    if (l.cin_pad % l.KC != 0) return fail(SCV_ERR_INVALID, "layer %s: Cin pad %d vs KC %d", l.name.c_str(), l.cin_pad, l.KC);
+  }
+  if ((int)a->layers.size() > SCV_MAX_LAYERS) return fail(SCV_ERR_INVALID, "too many layers");
+  return SCV_OK;
+}
+
+// ============================================================== engine
+struct Plan {
+  int B, H, W;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<void*> buf_ptr;
+  std::vector<ConvLaunch> launches;
+};
+
+struct scv_engine {
+  Arch arch;
+  int device = 0;
+  bool weights_set = false;
+  std::vector<float> h_head_w, h_head_b;
+  float* d_head_w = nullptr;
+  float* d_head_b = nullptr;
+  int* d_err = nullptr;
+  cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+  std::vector<std::unique_ptr<Plan>> plans;
+  // scratch
+  void* d_scene = nullptr;
+  size_t scene_bytes = 0;
+  float* d_prob = nullptr;
+  size_t prob_bytes = 0;
+  uint8_t* d_mask = nullptr;
+  size_t mask_bytes = 0;
+  int2* d_origins = nullptr;
+  size_t origins_cap = 0;
+  float* d_tile_stats = nullptr;
+  size_t tile_stats_cap = 0;
+  void* d_stage = nullptr;  // raw tiles staging for predict_tiles / predict_patches
+  size_t stage_bytes = 0;
+  float* d_tile_probs = nullptr;
+  size_t tile_probs_bytes = 0;
+  int32_t* d_tile_classes = nullptr;
+  size_t tile_classes_bytes = 0;
+  // options
+  int opt_profile_layers = 0;
+  int opt_stages = 0;
+  int opt_watchdog_ms = 2000;
+  // timing
+  std::vector<cudaEvent_t> ev_pool;
+  struct BatchEv {
+    int e0, e1, e2, e3;
+    std::vector<int> layer_ev;
+    int ntiles;
+  };
+  std::vector<BatchEv> batch_ev;
+  int n_launches = 0;
+  int last_side = 0;
+  bool times_pending = false;
+  scv_times times{};
+};
+
+static int dtype_bytes(int dt) {
+  switch (dt) {
+    case SCV_U8: return 1;
+    case SCV_U16:
+    case SCV_I16: return 2;
+    case SCV_F32: return 4;
+    case SCV_F64: return 8;
+  }
+  return 0;
+}
+
+static int ensure(void** p, size_t* cap, size_t need) {
+  if (*cap >= need && *p) return SCV_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CUDA_TRY(cudaMalloc(p, need));
+  *cap = need;
+  return SCV_OK;
+}
+
+static int check_device_err(scv_engine* e) {
+  int h = 0;
+  CUDA_TRY(cudaMemcpy(&h, e->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h) {
+    cudaMemset(e->d_err, 0, sizeof(int));
+    return fail(SCV_ERR_KERNEL, "device watchdog tripped: a conv pipeline stalled for > %d ms", e->opt_watchdog_ms);
+  }
+  return SCV_OK;
+}
+
+// ---- weights ---------------------------------------------------------------
+static const float BN_EPS = 1e-3f;  // keras BatchNormalization default
+
+static int upload_layer(LayerDef& l, const std::vector<float>& w /*[ntotal][ktotal]*/, const std::vector<float>& bias,
+                        const std::vector<float>* skip_s, const std::vector<float>* skip_t) {
+  const int ntaps = l.kind == L_CONV3 ? 9 : 1;
+  const size_t ktotal = (size_t)ntaps * l.cin_pad;
+  std::vector<__nv_bfloat16> wb(w.size());
+  for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2bfloat16_rn(w[i]);
+  if (l.d_w) cudaFree(l.d_w);
+  if (l.d_bias) cudaFree(l.d_bias);
+  l.d_w = nullptr;
+  l.d_bias = nullptr;
+  CUDA_TRY(cudaMalloc(&l.d_w, wb.size() * 2));
+  CUDA_TRY(cudaMemcpy(l.d_w, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&l.d_bias, bias.size() * 4));
+  CUDA_TRY(cudaMemcpy(l.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+  if (skip_s) {
+    if (l.d_skip_s) cudaFree(l.d_skip_s);
+    if (l.d_skip_t) cudaFree(l.d_skip_t);
+    CUDA_TRY(cudaMalloc(&l.d_skip_s, skip_s->size() * 4));
+    CUDA_TRY(cudaMalloc(&l.d_skip_t, skip_t->size() * 4));
+    CUDA_TRY(cudaMemcpy(l.d_skip_s, skip_s->data(), skip_s->size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(l.d_skip_t, skip_t->data(), skip_t->size() * 4, cudaMemcpyHostToDevice));
+  }
+  return make_w_tmap(&l.tmB, l.d_w, (int)ktotal, l.ntotal, l.KC, l.BN);
+}
+
+// BN fold: s = gamma / sqrt(var + eps), t = beta - mean * s  (fp32, like keras inference)
+static void bn_affine(const scv_tensor* t, int gamma_idx, int offset, int n, std::vector<float>* s, std::vector<float>* sh) {
+  s->resize(n);
+  sh->resize(n);
+  const float *g = t[gamma_idx].data + offset, *b = t[gamma_idx + 1].data + offset, *m = t[gamma_idx + 2].data + offset,
+              *v = t[gamma_idx + 3].data + offset;
+  for (int i = 0; i < n; ++i) {
+    const float sc = g[i] / std::sqrt(v[i] + BN_EPS);
+    (*s)[i] = sc;
+    (*sh)[i] = b[i] - m[i] * sc;
+  }
+}
+
+static int fold_and_upload(scv_engine* e, const scv_tensor* t) {
+  Arch& a = e->arch;
+  for (auto& l : a.layers) {
+    const int ntaps = l.kind == L_CONV3 ? 9 : 1;
+    const size_t ktotal = (size_t)ntaps * l.cin_pad;
+    std::vector<float> w((size_t)l.ntotal * ktotal, 0.f), bias(l.ntotal, 0.f);
+    const float* K = t[l.w_kernel].data;
+    const float* Bv = t[l.w_bias].data;
+    if (l.kind == L_CONV3) {
+      std::vector<float> s, sh;
+      bn_affine(t, l.w_bn, 0, l.cout, &s, &sh);
+      // keras HWIO (3,3,Cin,Cout) -> [o][tap*cin_pad + c] with W' = W*s[o]
+      for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < l.cin_real; ++c) {
+          const float* src = K + ((size_t)tap * l.cin_real + c) * l.cout;
+          for (int o = 0; o < l.cout; ++o) w[(size_t)o * ktotal + (size_t)tap * l.cin_pad + c] = src[o] * s[o];
+        }
+      for (int o = 0; o < l.cout; ++o) bias[o] = Bv[o] * s[o] + sh[o];  // (b - mean)*s + beta
+      std::vector<float> ks, kt;
+      if (l.epi == EPI_POOL_SKIP) {
+        bn_affine(t, l.w_skip_bn, 0, l.cout, &ks, &kt);
+        SCV_TRY(upload_layer(l, w, bias, &ks, &kt));
+      } else {
+        SCV_TRY(upload_layer(l, w, bias, nullptr, nullptr));
+      }
+    } else {
+      // keras Conv2DTranspose kernel (2,2,F,Cin) -> rows (a*2+b)*F + o, K = Cin; the BN that follows the
+      // concat is folded on the up half: W' = W*s2[o], b' = b*s2[o] + t2[o]
+      const int F = l.cout;
+      std::vector<float> s2, t2;
+      bn_affine(t, l.w_up_bn, F, F, &s2, &t2);
+      for (int ab = 0; ab < 4; ++ab)
+        for (int o = 0; o < F; ++o) {
+          const float* src = K + ((size_t)ab * F + o) * l.cin_real;
+          float* dst = &w[((size_t)ab * F + o) * ktotal];
+          for (int c = 0; c < l.cin_real; ++c) dst[c] = src[c] * s2[o];
+          bias[(size_t)ab * F + o] = Bv[o] * s2[o] + t2[o];
+        }
+      SCV_TRY(upload_layer(l, w, bias, nullptr, nullptr));
+    }
+  }
+  // 1x1 head: kernel (1,1,F0,ncls) -> [c][k] fp32
+  const int hk = a.spec_index.at("head/kernel");
+  const int F0 = a.cfg.filters[0], ncls = a.cfg.nclasses;
+  e->h_head_w.assign(t[hk].data, t[hk].data + (size_t)F0 * ncls);
+  e->h_head_b.assign(t[hk + 1].data, t[hk + 1].data + ncls);
+  if (!e->d_head_w) CUDA_TRY(cudaMalloc(&e->d_head_w, (size_t)F0 * ncls * 4));
+  if (!e->d_head_b) CUDA_TRY(cudaMalloc(&e->d_head_b, (size_t)ncls * 4));
+  CUDA_TRY(cudaMemcpy(e->d_head_w, e->h_head_w.data(), (size_t)F0 * ncls * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->d_head_b, e->h_head_b.data(), (size_t)ncls * 4, cudaMemcpyHostToDevice));
+  return SCV_OK;
+}
+
+// ---- plans -------------------------------------------------------------------
+static int pick_stages(int KC, int BN, int iters, int override_stages) {
+  if (override_stages > 0) return std::max(1, std::min(override_stages, 12));
+  const int sb = conv_stage_bytes(KC, BN);
+  int st = (100 * 1024) / sb;  // ~2 CTAs per SM
+  st = std::max(2, std::min(st, 8));
+  return std::max(1, std::min(st, iters));
+}
+
+static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int in_pitch, int B, int h, int w,
+                       ConvLaunch* L) {
+  memset(L, 0, sizeof *L);
+  ConvParams& p = L->p;
+  p.N = B;
+  p.H = h;
+  p.W = w;
+  p.Cin = l.cin_pad;
+  p.ntaps = l.kind == L_CONV3 ? 9 : 1;
+  tile_box(w, &p.TW, &p.TH, &p.TN);
+  p.tiles_x = (w + p.TW - 1) / p.TW;
+  p.tiles_y = (h + p.TH - 1) / p.TH;
+  p.tiles_n = (B + p.TN - 1) / p.TN;
+  p.n_tiles_n = l.ntotal / l.BN;
+  const int iters = p.ntaps * (l.cin_pad / l.KC);
+  p.nstage = pick_stages(l.KC, l.BN, iters, e ? e->opt_stages : 0);
+  p.relu = 1;
+  p.bias = l.d_bias;
+  p.Cout = l.cout;
+  p.skip_s = l.d_skip_s;
+  p.skip_t = l.d_skip_t;
+  p.err = e ? e->d_err : nullptr;
+  p.watchdog_ns = (unsigned long long)(e ? e->opt_watchdog_ms : 2000) * 1000000ull;
+  L->KC = l.KC;
+  L->BN = l.BN;
+  L->EPI = l.epi;
+  L->grid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
+  L->tmB = l.tmB;
+  SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, p.TW, p.TH, p.TN));
+  return SCV_OK;
+}
+
+static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
+  for (auto& pl : e->plans)
+    if (pl->B == B && pl->H == H && pl->W == W) {
+      *out = pl.get();
+      return SCV_OK;
+    }
+  Arch& a = e->arch;
+  const int L = a.cfg.nlevels;
+  if (H % (1 << L) || W % (1 << L) || H <= 0 || W <= 0)
+    return fail(SCV_ERR_INVALID, "tile %dx%d: H and W must be positive multiples of %d", H, W, 1 << L);
+  // keep at most 3 plans alive (full batch, tail batch, one spare)
+  while (e->plans.size() >= 3) {
+    cudaStreamSynchronize(e->stream);
+    cudaFree(e->plans.front()->arena);
+    e->plans.erase(e->plans.begin());
+  }
+  auto pl = std::make_unique<Plan>();
+  pl->B = B;
+  pl->H = H;
+  pl->W = W;
+  std::vector<size_t> off(a.bufs.size());
+  size_t total = 0;
+  for (size_t i = 0; i < a.bufs.size(); ++i) {
+    const BufDef& b = a.bufs[i];
+    const size_t bytes = (size_t)B * (H >> b.level) * (W >> b.level) * b.channels * (b.f32 ? 4 : 2);
+    off[i] = total;
+    total += (bytes + 1023) & ~size_t(1023);
+  }
+  CUDA_TRY(cudaMalloc(&pl->arena, total));
+  pl->arena_bytes = total;
+  pl->buf_ptr.resize(a.bufs.size());
+  for (size_t i = 0; i < a.bufs.size(); ++i) pl->buf_ptr[i] = pl->arena + off[i];
+  for (auto& l : a.layers) {
+    ConvLaunch Ln;
+    const int h = H >> l.level, w = W >> l.level;
+    SCV_TRY(fill_launch(e, l, pl->buf_ptr[l.in_buf], a.bufs[l.in_buf].channels, B, h, w, &Ln));
+    ConvParams& p = Ln.p;
+    if (l.epi == EPI_HEAD) {
+      p.head_w = e->d_head_w;
+      p.head_b = e->d_head_b;
+      p.ncls = a.cfg.nclasses;
+      p.logits = (float*)pl->buf_ptr[l.out_buf];
+    } else {
+      p.out = (__nv_bfloat16*)pl->buf_ptr[l.out_buf];
+      p.out_pitch = a.bufs[l.out_buf].channels;
+      p.out_choff = l.out_choff;
+      if (l.epi == EPI_POOL_SKIP) {
+        p.pool_out = (__nv_bfloat16*)pl->buf_ptr[l.pool_buf];
+        p.pool_pitch = a.bufs[l.pool_buf].channels;
+      }
+    }
+    Ln.smem = conv_smem_bytes(l.KC, l.BN, p.nstage, l.epi, a.cfg.nclasses);
+    pl->launches.push_back(Ln);
+  }
+  *out = pl.get();
+  e->plans.push_back(std::move(pl));
+  return SCV_OK;
+}
+
+static int new_event(scv_engine* e, cudaStream_t s) {
+  static thread_local int dummy;
+  (void)dummy;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return -1;
+  cudaEventRecord(ev, s);
+  e->ev_pool.push_back(ev);
+  return (int)e->ev_pool.size() - 1;
+}
+
+static void reset_timing(scv_engine* e) {
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  e->ev_pool.clear();
+  e->batch_ev.clear();
+  e->n_launches = 0;
+  e->times_pending = false;
+}
+
+static int run_layers(scv_engine* e, Plan* pl, cudaStream_t s, scv_engine::BatchEv* bev) {
+  for (size_t i = 0; i < pl->launches.size(); ++i) {
+    if (e->opt_profile_layers && bev) bev->layer_ev.push_back(new_event(e, s));
+    cudaError_t err = conv_launch(pl->launches[i], s);
+    if (err != cudaSuccess)
+      return fail(SCV_ERR_CUDA, "launch of layer %s failed: %s", e->arch.layers[i].name.c_str(), cudaGetErrorString(err));
+    e->n_launches++;
+  }
+  if (e->opt_profile_layers && bev) bev->layer_ev.push_back(new_event(e, s));
+  return SCV_OK;
+}
+
+static int finalize_times(scv_engine* e) {
+  if (!e->times_pending) return SCV_OK;
+  scv_times& t = e->times;
+  memset(&t, 0, sizeof t);
+  t.n_layers = (int)e->arch.layers.size();
+  for (size_t i = 0; i < e->arch.layers.size(); ++i) {
+    const LayerDef& l = e->arch.layers[i];
+    const double px = (double)(e->last_side >> l.level) * (e->last_side >> l.level);
+    t.layer_flops[i] = l.flops_per_tile_at_unit * px;
+  }
+  if (!e->batch_ev.empty()) {
+    CUDA_TRY(cudaEventSynchronize(e->ev_pool[e->batch_ev.back().e3]));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->ev_pool[e->batch_ev.front().e0], e->ev_pool[e->batch_ev.back().e3]));
+    t.total_ms = ms;
+    for (auto& b : e->batch_ev) {
+      cudaEventElapsedTime(&ms, e->ev_pool[b.e0], e->ev_pool[b.e1]);
+      t.extract_ms += ms;
+      cudaEventElapsedTime(&ms, e->ev_pool[b.e1], e->ev_pool[b.e2]);
+      t.network_ms += ms;
+      cudaEventElapsedTime(&ms, e->ev_pool[b.e2], e->ev_pool[b.e3]);
+      t.stitch_ms += ms;
+      t.n_tiles += b.ntiles;
+      for (size_t i = 0; i + 1 < b.layer_ev.size() && i < SCV_MAX_LAYERS; ++i) {
+        cudaEventElapsedTime(&ms, e->ev_pool[b.layer_ev[i]], e->ev_pool[b.layer_ev[i + 1]]);
+        t.layer_ms[i] += ms;
+      }
+    }
+    t.n_batches = (int)e->batch_ev.size();
+  }
+  t.n_launches = e->n_launches;
+  e->times_pending = false;
+  return SCV_OK;
+}
+
+// ---- shared batch pipeline ------------------------------------------------------
+struct TileJob {
+  // source (mosaic or stacked tiles, device resident)
+  const void* d_src;
+  size_t src_bytes;
+  int dtype, src_W, C, src_row0;
+  int side;
+  const int2* d_src_origins;  // n tiles
+  const scv_norm* norm;
+  // destination: stitched raster ...
+  const int2* d_dst_origins;  // n tiles (null -> per-tile outputs)
+  int kernel, crop, out_W, dst_row0, out_channel, force_scalar;
+  float* d_prob;
+  uint8_t* d_mask;
+  // ... or whole tiles
+  float* d_tile_probs;
+  int32_t* d_tile_classes;
+};
+
+static int norm_to_params(const scv_norm* n, int C, ExtractParams* ep) {
+  ep->norm_mode = n ? n->mode : SCV_NORM_NONE;
+  for (int c = 0; c < SCV_MAX_BANDS; ++c) {
+    ep->sub[c] = 0.f;
+    ep->div[c] = 1.f;
+  }
+  if (!n || n->mode == SCV_NORM_NONE) return SCV_OK;
+  if (n->mode < 0 || n->mode > SCV_NORM_TILE_MINMAX) return fail(SCV_ERR_INVALID, "unknown norm mode %d", n->mode);
+  if (n->mode == SCV_NORM_PER_BAND) {
+    if (n->nbands != C) return fail(SCV_ERR_INVALID, "norm has %d bands, input has %d", n->nbands, C);
+    for (int c = 0; c < C; ++c) {
+      ep->sub[c] = n->sub[c];
+      ep->div[c] = n->div[c];
+    }
+  } else {
+    ep->div[0] = n->div[0];  // epsilon
+  }
+  return SCV_OK;
+}
+
+// Runs tiles [t0, t0+nb) of the job through extract -> network -> stitch/head on `s`.
+static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStream_t s) {
+  Plan* pl = nullptr;
+  SCV_TRY(get_plan(e, nb, job.side, job.side, &pl));
+  e->last_side = job.side;
+  Arch& a = e->arch;
+  scv_engine::BatchEv bev{};
+  bev.ntiles = nb;
+  bev.e0 = new_event(e, s);
+
+  ExtractParams ep{};
+  ep.src = (const uint8_t*)job.d_src;
+  ep.src_bytes = job.src_bytes;
+  ep.dtype = job.dtype;
+  ep.W = job.src_W;
+  ep.C = job.C;
+  ep.src_row0 = job.src_row0;
+  ep.origins = job.d_src_origins + t0;
+  ep.n_tiles = nb;
+  ep.side = job.side;
+  ep.cpad = a.c0pad;
+  SCV_TRY(norm_to_params(job.norm, job.C, &ep));
+  const int row_bytes = job.side * job.C * dtype_bytes(job.dtype);
+  ep.rows_per_block = std::max(1, std::min(8, (44 * 1024) / (row_bytes + 32)));
+  ep.out = (__nv_bfloat16*)pl->buf_ptr[a.x0_buf];
+  if (ep.norm_mode == SCV_NORM_TILE_ZSCORE || ep.norm_mode == SCV_NORM_TILE_MINMAX) {
+    SCV_TRY(ensure((void**)&e->d_tile_stats, &e->tile_stats_cap, (size_t)nb * job.C * 2 * sizeof(float)));
+    TileStatsParams sp{};
+    sp.src = ep.src;
+    sp.dtype = job.dtype;
+    sp.W = job.src_W;
+    sp.C = job.C;
+    sp.src_row0 = job.src_row0;
+    sp.origins = ep.origins;
+    sp.side = job.side;
+    sp.mode = ep.norm_mode;
+    sp.eps = ep.div[0];
+    sp.stats = e->d_tile_stats;
+    CUDA_TRY(launch_tile_stats(sp, nb, s));
+    e->n_launches++;
+    ep.tile_stats = e->d_tile_stats;
+  }
+  if (extract_smem_bytes(ep) > 160 * 1024) return fail(SCV_ERR_INVALID, "tile row of %d bytes too large for the extract kernel", row_bytes);
+  CUDA_TRY(launch_extract(ep, s));
+  e->n_launches++;
+  bev.e1 = new_event(e, s);
+
+  SCV_TRY(run_layers(e, pl, s, &bev));
+  bev.e2 = new_event(e, s);
+
+  const float* logits = (const float*)pl->buf_ptr[a.logits_buf];
+  if (job.d_dst_origins) {
+    StitchParams sp{};
+    sp.logits = logits;
+    sp.side = job.side;
+    sp.ncls = a.cfg.nclasses;
+    sp.head = a.cfg.head;
+    sp.threshold = a.cfg.threshold;
+    sp.out_channel = job.out_channel;
+    sp.crop = job.crop;
+    sp.kernel = job.kernel;
+    sp.dst_origins = job.d_dst_origins + t0;
+    sp.force_scalar = job.force_scalar;
+    sp.dst_row0 = job.dst_row0;
+    sp.out_W = job.out_W;
+    sp.prob = job.d_prob;
+    sp.mask = job.d_mask;
+    CUDA_TRY(launch_stitch(sp, nb, s));
+  } else {
+    HeadTilesParams hp{};
+    hp.logits = logits;
+    hp.npix = (long long)nb * job.side * job.side;
+    hp.ncls = a.cfg.nclasses;
+    hp.head = a.cfg.head;
+    hp.threshold = a.cfg.threshold;
+    const size_t tile_px = (size_t)job.side * job.side;
+    hp.probs = job.d_tile_probs ? job.d_tile_probs + (size_t)t0 * tile_px * a.cfg.nclasses : nullptr;
+    hp.classes = job.d_tile_classes ? job.d_tile_classes + (size_t)t0 * tile_px : nullptr;
+    CUDA_TRY(launch_head_tiles(hp, s));
+  }
+  e->n_launches++;
+  bev.e3 = new_event(e, s);
+  e->batch_ev.push_back(bev);
+  return SCV_OK;
+}
+
+static void balanced_batches(int n, int maxb, std::vector<int>* sizes) {
+  sizes->clear();
+  if (n <= 0) return;
+  const int nb = (n + maxb - 1) / maxb;
+  const int base = n / nb, extra = n % nb;
+  for (int i = 0; i < nb; ++i) sizes->push_back(base + (i < extra ? 1 : 0));
+}
+
+// generate_chip_indices (utils/prediction_tools.py:87-109): y in range(buff/2, H-(buff+kernel), kernel)
+static void chip_grid(int H, int W, const scv_tiling* t, std::vector<int>* ys, std::vector<int>* xs) {
+  const int side = t->buff + t->kernel, half = t->buff / 2;
+  for (int y = half; y < H - side; y += t->kernel) ys->push_back(y);
+  for (int x = half; x < W - side; x += t->kernel) xs->push_back(x);
+}
+
+static int check_tiling(const scv_engine* e, const scv_tiling* t) {
+  if (!t || t->kernel <= 0 || t->buff < 0 || (t->buff & 1))
+    return fail(SCV_ERR_INVALID, "tiling: kernel must be > 0 and buff a non-negative even number");
+  const int side = t->kernel + t->buff;
+  if (side % (1 << e->arch.cfg.nlevels))
+    return fail(SCV_ERR_INVALID, "tile side kernel+buff=%d must be a multiple of %d", side, 1 << e->arch.cfg.nlevels);
+  return SCV_OK;
+}
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* scv_version(void) { return "scv-b200 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+const char* scv_last_error(void) { return g_err.c_str(); }
+
+int scv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int scv_num_weights(const scv_config* cfg) {
+  if (validate_config(cfg) != SCV_OK) return SCV_ERR_INVALID;
+  std::vector<WeightSpec> s;
+  build_specs(cfg, &s);
+  return (int)s.size();
+}
+
+int scv_weight_shape(const scv_config* cfg, int index, int* ndim, int64_t shape[4], char* name, int name_len) {
+  SCV_TRY(validate_config(cfg));
+  std::vector<WeightSpec> s;
+  build_specs(cfg, &s);
+  if (index < 0 || index >= (int)s.size()) return fail(SCV_ERR_INVALID, "weight index %d out of range", index);
+  if (ndim) *ndim = s[index].ndim;
+  if (shape)
+    for (int i = 0; i < 4; ++i) shape[i] = s[index].shape[i];
+  if (name && name_len > 0) snprintf(name, name_len, "%s", s[index].name.c_str());
+  return SCV_OK;
+}
+
+int scv_engine_create(const scv_config* cfg, scv_engine** out) {
+  if (!out) return fail(SCV_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  SCV_TRY(validate_config(cfg));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SCV_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SCV_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(SCV_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  auto e = std::make_unique<scv_engine>();
+  SCV_TRY(build_arch(cfg, &e->arch));
+  if (e->arch.cfg.max_batch <= 0) e->arch.cfg.max_batch = 64;
+  e->device = cfg->device;
+  CUDA_TRY(conv_init_attributes());
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&e->d_err, sizeof(int)));
+  CUDA_TRY(cudaMemset(e->d_err, 0, sizeof(int)));
+  *out = e.release();
+  return SCV_OK;
+}
+
+void scv_engine_destroy(scv_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  reset_timing(e);
+  for (auto& pl : e->plans) cudaFree(pl->arena);
+  for (auto& l : e->arch.layers) {
+    cudaFree(l.d_w);
+    cudaFree(l.d_bias);
+    cudaFree(l.d_skip_s);
+    cudaFree(l.d_skip_t);
+  }
+  cudaFree(e->d_head_w);
+  cudaFree(e->d_head_b);
+  cudaFree(e->d_err);
+  cudaFree(e->d_scene);
+  cudaFree(e->d_prob);
+  cudaFree(e->d_mask);
+  cudaFree(e->d_origins);
+  cudaFree(e->d_tile_stats);
+  cudaFree(e->d_stage);
+  cudaFree(e->d_tile_probs);
+  cudaFree(e->d_tile_classes);
+  cudaStreamDestroy(e->stream);
+  cudaStreamDestroy(e->h2d);
+  cudaStreamDestroy(e->d2h);
+  delete e;
+}
+
+int scv_engine_set_weights(scv_engine* e, const scv_tensor* tensors, int n) {
+  if (!e || !tensors) return fail(SCV_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const auto& specs = e->arch.specs;
+  if (n != (int)specs.size()) return fail(SCV_ERR_INVALID, "expected %d weight arrays, got %d", (int)specs.size(), n);
+  for (int i = 0; i < n; ++i) {
+    if (!tensors[i].data) return fail(SCV_ERR_INVALID, "weight %d (%s) has NULL data", i, specs[i].name.c_str());
+    if (tensors[i].ndim != specs[i].ndim) return fail(SCV_ERR_INVALID, "weight %d (%s): ndim %d, expected %d", i, specs[i].name.c_str(), tensors[i].ndim, specs[i].ndim);
+    for (int d = 0; d < specs[i].ndim; ++d)
+      if (tensors[i].shape[d] != specs[i].shape[d])
+        return fail(SCV_ERR_INVALID, "weight %d (%s): dim %d is %lld, expected %lld", i, specs[i].name.c_str(), d, (long long)tensors[i].shape[d], (long long)specs[i].shape[d]);
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  SCV_TRY(fold_and_upload(e, tensors));
+  // weight pointers / tensor maps are baked into the plans
+  for (auto& pl : e->plans) cudaFree(pl->arena);
+  e->plans.clear();
+  e->weights_set = true;
+  return SCV_OK;
+}
+
+int scv_set_option(scv_engine* e, const char* key, int value) {
+  if (!e || !key) return fail(SCV_ERR_INVALID, "NULL argument");
+  const std::string k(key);
+  if (k == "profile_layers") e->opt_profile_layers = value;
+  else if (k == "stages") {
+    e->opt_stages = value;
+    cudaStreamSynchronize(e->stream);
+    for (auto& pl : e->plans) cudaFree(pl->arena);
+    e->plans.clear();
+  } else if (k == "watchdog_ms") e->opt_watchdog_ms = value;
+  else if (k == "max_batch") e->arch.cfg.max_batch = std::max(1, value);
+  else return fail(SCV_ERR_INVALID, "unknown option '%s'", key);
+  return SCV_OK;
+}
+
+int scv_get_times(scv_engine* e, scv_times* out) {
+  if (!e || !out) return fail(SCV_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(e->device));
+  SCV_TRY(finalize_times(e));
+  *out = e->times;
+  return SCV_OK;
+}
+
+void* scv_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    g_err = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+void scv_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+static int precheck(scv_engine* e, int dtype, int C) {
+  if (!e) return fail(SCV_ERR_INVALID, "engine is NULL");
+  if (!e->weights_set) return fail(SCV_ERR_STATE, "predict called before scv_engine_set_weights");
+  if (dtype_bytes(dtype) == 0) return fail(SCV_ERR_INVALID, "unknown dtype %d", dtype);
+  if (C != e->arch.cfg.nchannels) return fail(SCV_ERR_INVALID, "input has %d bands, model expects %d", C, e->arch.cfg.nchannels);
+  CUDA_TRY(cudaSetDevice(e->device));
+  return SCV_OK;
+}
+
+int scv_predict_mosaic_device(scv_engine* e, const void* d_hwc, int dtype, int H, int W, int C, int src_row0,
+                              const scv_tiling* tiling, const scv_norm* norm, int tile_row_begin, int tile_row_end,
+                              int out_channel, float* d_prob, uint8_t* d_mask, int dst_row0, void* stream) {
+  SCV_TRY(precheck(e, dtype, C));
+  SCV_TRY(check_tiling(e, tiling));
+  if (!d_hwc) return fail(SCV_ERR_INVALID, "d_hwc is NULL");
+  if (out_channel < 0 || out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", out_channel);
+  std::vector<int> ys, xs;
+  chip_grid(H, W, tiling, &ys, &xs);
+  const int nrows = (int)ys.size();
+  if (tile_row_end < 0 || tile_row_end > nrows) tile_row_end = nrows;
+  tile_row_begin = std::max(0, tile_row_begin);
+  reset_timing(e);
+  e->times_pending = true;
+  if (tile_row_begin >= tile_row_end || xs.empty()) return SCV_OK;  // empty chip list: nothing predicted
+  const int half = tiling->buff / 2, side = tiling->kernel + tiling->buff;
+  const int n = (tile_row_end - tile_row_begin) * (int)xs.size();
+  std::vector<int2> org(2 * (size_t)n);
+  int force_scalar = 0;
+  {
+    int k = 0;
+    for (int r = tile_row_begin; r < tile_row_end; ++r)
+      for (int x : xs) {
+        org[k] = make_int2(x - half, ys[r] - half);
+        org[n + k] = make_int2(x, ys[r]);
+        if (x & 3) force_scalar = 1;
+        ++k;
+      }
+  }
+  if (ys[tile_row_begin] - half < src_row0) return fail(SCV_ERR_INVALID, "src_row0=%d is below the first needed mosaic row %d", src_row0, ys[tile_row_begin] - half);
+  if (ys[tile_row_begin] < dst_row0) return fail(SCV_ERR_INVALID, "dst_row0=%d is below the first written row %d", dst_row0, ys[tile_row_begin]);
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, org.size() * sizeof(int2)));
+  CUDA_TRY(cudaMemcpyAsync(e->d_origins, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // org is a stack-lifetime host vector
+
+  TileJob job{};
+  job.d_src = d_hwc;
+  const int last_row = ys[tile_row_end - 1] - half + side;  // exclusive
+  job.src_bytes = (size_t)(last_row - src_row0) * W * C * dtype_bytes(dtype);
+  job.dtype = dtype;
+  job.src_W = W;
+  job.C = C;
+  job.src_row0 = src_row0;
+  job.side = side;
+  job.d_src_origins = e->d_origins;
+  job.norm = norm;
+  job.d_dst_origins = e->d_origins + n;
+  job.kernel = tiling->kernel;
+  job.crop = half;
+  job.out_W = W;
+  job.dst_row0 = dst_row0;
+  job.out_channel = out_channel;
+  job.force_scalar = force_scalar;
+  job.d_prob = d_prob;
+  job.d_mask = d_mask;
+  std::vector<int> sizes;
+  balanced_batches(n, e->arch.cfg.max_batch, &sizes);
+  int t0 = 0;
+  for (int nb : sizes) {
+    SCV_TRY(run_batch(e, job, t0, nb, s));
+    t0 += nb;
+  }
+  if (!stream) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    SCV_TRY(check_device_err(e));
+  }
+  return SCV_OK;
+}
+
+int scv_predict_mosaic(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
+                       const scv_norm* norm, int tile_row_begin, int tile_row_end, int out_channel, float* out_prob,
+                       uint8_t* out_mask) {
+  SCV_TRY(precheck(e, dtype, C));
+  SCV_TRY(check_tiling(e, tiling));
+  if (!hwc || !out_prob) return fail(SCV_ERR_INVALID, "NULL buffer");
+  if (out_channel < 0 || out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", out_channel);
+  std::vector<int> ys, xs;
+  chip_grid(H, W, tiling, &ys, &xs);
+  const int nrows = (int)ys.size(), ncols = (int)xs.size();
+  if (tile_row_end < 0 || tile_row_end > nrows) tile_row_end = nrows;
+  tile_row_begin = std::max(0, tile_row_begin);
+  reset_timing(e);
+  e->times_pending = true;
+  if (tile_row_begin >= tile_row_end || ncols == 0) return SCV_OK;
+  const int half = tiling->buff / 2, side = tiling->kernel + tiling->buff, K = tiling->kernel;
+  const int es = dtype_bytes(dtype);
+  const size_t row_bytes = (size_t)W * C * es;
+  const int src_row0 = ys[tile_row_begin] - half;
+  const int src_row1 = ys[tile_row_end - 1] - half + side;
+  const int dst_row0 = ys[tile_row_begin];
+  const int dst_rows = (tile_row_end - tile_row_begin) * K;
+  SCV_TRY(ensure(&e->d_scene, &e->scene_bytes, (size_t)(src_row1 - src_row0) * row_bytes));
+  SCV_TRY(ensure((void**)&e->d_prob, &e->prob_bytes, (size_t)dst_rows * W * sizeof(float)));
+  if (out_mask) SCV_TRY(ensure((void**)&e->d_mask, &e->mask_bytes, (size_t)dst_rows * W));
+
+  const int n = (tile_row_end - tile_row_begin) * ncols;
+  std::vector<int2> org(2 * (size_t)n);
+  int force_scalar = 0;
+  {
+    int k = 0;
+    for (int r = tile_row_begin; r < tile_row_end; ++r)
+      for (int x : xs) {
+        org[k] = make_int2(x - half, ys[r] - half);
+        org[n + k] = make_int2(x, ys[r]);
+        if (x & 3) force_scalar = 1;
+        ++k;
+      }
+  }
+  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, org.size() * sizeof(int2)));
+  CUDA_TRY(cudaMemcpyAsync(e->d_origins, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+
+  // H2D: one chunk per tile row (the K new mosaic rows it needs; the first also brings the top buffer),
+  // all enqueued up front on the copy stream so PCIe runs back to back while compute starts on chunk 0.
+  const int ntr = tile_row_end - tile_row_begin;
+  std::vector<cudaEvent_t> up_ev(ntr), done_ev;
+  int uploaded = src_row0;
+  for (int r = 0; r < ntr; ++r) {
+    const int need = ys[tile_row_begin + r] - half + side;  // exclusive
+    const uint8_t* hsrc = (const uint8_t*)hwc + (size_t)uploaded * row_bytes;
+    uint8_t* ddst = (uint8_t*)e->d_scene + (size_t)(uploaded - src_row0) * row_bytes;
+    CUDA_TRY(cudaMemcpyAsync(ddst, hsrc, (size_t)(need - uploaded) * row_bytes, cudaMemcpyHostToDevice, e->h2d));
+    uploaded = need;
+    CUDA_TRY(cudaEventCreateWithFlags(&up_ev[r], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(up_ev[r], e->h2d));
+  }
+
+  TileJob job{};
+  job.d_src = e->d_scene;
+  job.src_bytes = (size_t)(src_row1 - src_row0) * row_bytes;
+  job.dtype = dtype;
+  job.src_W = W;
+  job.C = C;
+  job.src_row0 = src_row0;
+  job.side = side;
+  job.d_src_origins = e->d_origins;
+  job.norm = norm;
+  job.d_dst_origins = e->d_origins + n;
+  job.kernel = K;
+  job.crop = half;
+  job.out_W = W;
+  job.dst_row0 = dst_row0;
+  job.out_channel = out_channel;
+  job.force_scalar = force_scalar;
+  job.d_prob = e->d_prob;
+  job.d_mask = out_mask ? e->d_mask : nullptr;
+
+  std::vector<int> sizes;
+  balanced_batches(n, e->arch.cfg.max_batch, &sizes);
+  int t0 = 0, rows_downloaded = 0, rows_waited = 0;
+  int rc = SCV_OK;
+  const size_t core_w = (size_t)ncols * K;
+  for (int nb : sizes) {
+    const int last_tile_row = (t0 + nb - 1) / ncols;  // relative tile row this batch reaches
+    for (; rows_waited <= last_tile_row; ++rows_waited) cudaStreamWaitEvent(e->stream, up_ev[rows_waited], 0);
+    if ((rc = run_batch(e, job, t0, nb, e->stream)) != SCV_OK) break;
+    t0 += nb;
+    // D2H of the tile rows completed so far (cores only: columns [xs[0], xs[0]+ncols*K))
+    const int complete = t0 / ncols;
+    if (complete > rows_downloaded) {
+      cudaEvent_t ev;
+      cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      cudaEventRecord(ev, e->stream);
+      cudaStreamWaitEvent(e->d2h, ev, 0);
+      done_ev.push_back(ev);
+      const int r0 = rows_downloaded * K, nr = (complete - rows_downloaded) * K;
+      const size_t doff = (size_t)r0 * W + xs[0];
+      const size_t hoff = (size_t)(dst_row0 + r0) * W + xs[0];
+      cudaMemcpy2DAsync(out_prob + hoff, (size_t)W * 4, e->d_prob + doff, (size_t)W * 4, core_w * 4, nr,
+                        cudaMemcpyDeviceToHost, e->d2h);
+      if (out_mask)
+        cudaMemcpy2DAsync(out_mask + hoff, (size_t)W, e->d_mask + doff, (size_t)W, core_w, nr, cudaMemcpyDeviceToHost,
+                          e->d2h);
+      rows_downloaded = complete;
+    }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(e->stream);
+  cudaError_t e2 = cudaStreamSynchronize(e->d2h);
+  cudaError_t e3 = cudaStreamSynchronize(e->h2d);
+  for (auto ev : up_ev) cudaEventDestroy(ev);
+  for (auto ev : done_ev) cudaEventDestroy(ev);
+  if (rc != SCV_OK) return rc;
+  CUDA_TRY(e1);
+  CUDA_TRY(e2);
+  CUDA_TRY(e3);
+  SCV_TRY(check_device_err(e));
+  return SCV_OK;
+}
+
+// shared by predict_tiles / predict_patches: upload stacked patches batch by batch
+static int run_stacked(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C, const scv_norm* norm,
+                       TileJob job, float* h_probs, int32_t* h_classes) {
+  if (H != W) return fail(SCV_ERR_INVALID, "patches must be square (got %dx%d)", H, W);
+  const int es = dtype_bytes(dtype);
+  const size_t tile_bytes = (size_t)H * W * C * es;
+  const size_t tile_px = (size_t)H * W;
+  const int ncls = e->arch.cfg.nclasses;
+  std::vector<int> sizes;
+  balanced_batches(N, e->arch.cfg.max_batch, &sizes);
+  const int maxb = sizes.empty() ? 0 : sizes[0];
+  SCV_TRY(ensure(&e->d_stage, &e->stage_bytes, (size_t)maxb * tile_bytes));
+  std::vector<int2> org((size_t)maxb);
+  for (int i = 0; i < maxb; ++i) org[i] = make_int2(0, i * H);
+  // origins layout: [maxb stacked-source origins][N destination origins] (the latter filled by the caller)
+  CUDA_TRY(cudaMemcpyAsync(e->d_origins, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+  job.d_src = e->d_stage;
+  job.dtype = dtype;
+  job.src_W = W;
+  job.C = C;
+  job.src_row0 = 0;
+  job.side = H;
+  job.norm = norm;
+  int t0 = 0;
+  for (int nb : sizes) {
+    CUDA_TRY(cudaMemcpyAsync(e->d_stage, (const uint8_t*)nhwc + (size_t)t0 * tile_bytes, (size_t)nb * tile_bytes,
+                             cudaMemcpyHostToDevice, e->stream));
+    job.src_bytes = (size_t)nb * tile_bytes;
+    // run_batch offsets origin arrays and per-tile outputs by t0: compensate for the per-batch staging
+    TileJob bj = job;
+    bj.d_src_origins = e->d_origins - t0;
+    SCV_TRY(run_batch(e, bj, t0, nb, e->stream));
+    if (h_probs)
+      CUDA_TRY(cudaMemcpyAsync(h_probs + (size_t)t0 * tile_px * ncls, e->d_tile_probs + (size_t)t0 * tile_px * ncls,
+                               (size_t)nb * tile_px * ncls * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h_classes)
+      CUDA_TRY(cudaMemcpyAsync(h_classes + (size_t)t0 * tile_px, e->d_tile_classes + (size_t)t0 * tile_px,
+                               (size_t)nb * tile_px * 4, cudaMemcpyDeviceToHost, e->stream));
+    t0 += nb;
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  SCV_TRY(check_device_err(e));
+  return SCV_OK;
+}
+
+int scv_predict_tiles(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C, const scv_norm* norm,
+                      float* probs, int32_t* classes) {
+  SCV_TRY(precheck(e, dtype, C));
+  if (!nhwc) return fail(SCV_ERR_INVALID, "nhwc is NULL");
+  if (N < 0) return fail(SCV_ERR_INVALID, "N < 0");
+  reset_timing(e);
+  e->times_pending = true;
+  if (N == 0) return SCV_OK;
+  const size_t tile_px = (size_t)H * W;
+  const int ncls = e->arch.cfg.nclasses;
+  if (probs) SCV_TRY(ensure((void**)&e->d_tile_probs, &e->tile_probs_bytes, (size_t)N * tile_px * ncls * 4));
+  if (classes) SCV_TRY(ensure((void**)&e->d_tile_classes, &e->tile_classes_bytes, (size_t)N * tile_px * 4));
+  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, (size_t)(e->arch.cfg.max_batch + 1) * sizeof(int2)));
+  TileJob job{};
+  job.d_dst_origins = nullptr;
+  job.d_tile_probs = probs ? e->d_tile_probs : nullptr;
+  job.d_tile_classes = classes ? e->d_tile_classes : nullptr;
+  return run_stacked(e, nhwc, dtype, N, H, W, C, norm, job, probs, classes);
+}
+
+int scv_predict_patches(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C,
+                        const scv_tiling* tiling, const scv_norm* norm, int cols, int out_channel, float* out_prob,
+                        uint8_t* out_mask) {
+  SCV_TRY(precheck(e, dtype, C));
+  SCV_TRY(check_tiling(e, tiling));
+  if (!nhwc || !out_prob) return fail(SCV_ERR_INVALID, "NULL buffer");
+  const int side = tiling->kernel + tiling->buff, K = tiling->kernel;
+  if (H != side || W != side) return fail(SCV_ERR_INVALID, "patches are %dx%d but kernel+buff=%d", H, W, side);
+  if (cols <= 0 || N % cols) return fail(SCV_ERR_INVALID, "N=%d patches do not fill rows of %d", N, cols);
+  if (out_channel < 0 || out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", out_channel);
+  reset_timing(e);
+  e->times_pending = true;
+  if (N == 0) return SCV_OK;
+  const int rows = N / cols;
+  const size_t out_px = (size_t)rows * K * cols * K;
+  SCV_TRY(ensure((void**)&e->d_prob, &e->prob_bytes, out_px * 4));
+  if (out_mask) SCV_TRY(ensure((void**)&e->d_mask, &e->mask_bytes, out_px));
+  const int maxb = e->arch.cfg.max_batch;
+  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, (size_t)(maxb + N + 1) * sizeof(int2)));
+  std::vector<int2> dst((size_t)N);
+  for (int i = 0; i < N; ++i) dst[i] = make_int2((i % cols) * K, (i / cols) * K);
+  CUDA_TRY(cudaMemcpy(e->d_origins + maxb, dst.data(), dst.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  TileJob job{};
+  job.d_dst_origins = e->d_origins + maxb;
+  job.kernel = K;
+  job.crop = tiling->buff / 2;
+  job.out_W = cols * K;
+  job.dst_row0 = 0;
+  job.out_channel = out_channel;
+  job.force_scalar = (K & 3) ? 1 : 0;
+  job.d_prob = e->d_prob;
+  job.d_mask = out_mask ? e->d_mask : nullptr;
+  SCV_TRY(run_stacked(e, nhwc, dtype, N, H, W, C, norm, job, nullptr, nullptr));
+  CUDA_TRY(cudaMemcpy(out_prob, e->d_prob, out_px * 4, cudaMemcpyDeviceToHost));
+  if (out_mask) CUDA_TRY(cudaMemcpy(out_mask, e->d_mask, out_px, cudaMemcpyDeviceToHost));
+  return SCV_OK;
+}
+
+// ------------------------------------------------------------------ debug entries
+static int debug_common_begin(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SCV_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(conv_init_attributes());
+  return SCV_OK;
+}
+
+static int debug_conv(int device, int kind, const float* x, int N, int H, int W, int Cin, const float* kernel,
+                      const float* bias, int Cout, int relu, float* y, float* pooled) {
+  SCV_TRY(debug_common_begin(device));
+  LayerDef l{};
+  l.name = "debug";
+  l.kind = kind;
+  l.epi = kind == L_CONVT ? EPI_CONVT : (pooled ? EPI_POOL_SKIP : EPI_STORE);
+  l.cin_real = Cin;
+  l.cin_pad = pad_channels(Cin);
+  l.cout = Cout;
+  l.ntotal = kind == L_CONVT ? 4 * Cout : Cout;
+  l.KC = kc_for(l.cin_pad);
+  l.BN = bn_for(l.ntotal);
+  if (const char* s = getenv("SCV_DEBUG_BN")) {
+    const int bn = atoi(s);
+    if (bn > 0 && l.ntotal % bn == 0) l.BN = bn;
+  }
+  if (l.BN == 0) return fail(SCV_ERR_INVALID, "Cout=%d unsupported (needs a multiple of 32)", Cout);
+  const int ntaps = kind == L_CONV3 ? 9 : 1;
+  const size_t ktotal = (size_t)ntaps * l.cin_pad;
+  std::vector<float> w((size_t)l.ntotal * ktotal, 0.f), b(l.ntotal, 0.f);
+  if (kind == L_CONV3) {
+    for (int tap = 0; tap < 9; ++tap)
+      for (int c = 0; c < Cin; ++c)
+        for (int o = 0; o < Cout; ++o) w[(size_t)o * ktotal + (size_t)tap * l.cin_pad + c] = kernel[((size_t)tap * Cin + c) * Cout + o];
+    for (int o = 0; o < Cout; ++o) b[o] = bias[o];
+  } else {
+    for (int ab = 0; ab < 4; ++ab)
+      for (int o = 0; o < Cout; ++o) {
+        for (int c = 0; c < Cin; ++c) w[((size_t)ab * Cout + o) * ktotal + c] = kernel[((size_t)ab * Cout + o) * Cin + c];
+        b[(size_t)ab * Cout + o] = bias[o];
+      }
+  }
+  std::vector<float> ones(l.ntotal, 1.f), zeros(l.ntotal, 0.f);
+  int rc = upload_layer(l, w, b, pooled ? &ones : nullptr, pooled ? &zeros : nullptr);
+  // input: pad channels, round to bf16
+  const size_t npix = (size_t)N * H * W;
+  std::vector<__nv_bfloat16> xin(npix * l.cin_pad, __float2bfloat16_rn(0.f));
+  for (size_t p = 0; p < npix; ++p)
+    for (int c = 0; c < Cin; ++c) xin[p * l.cin_pad + c] = __float2bfloat16_rn(x[p * Cin + c]);
+  const int oh = kind == L_CONVT ? 2 * H : H, ow = kind == L_CONVT ? 2 * W : W;
+  const size_t nout = (size_t)N * oh * ow * Cout;
+  const size_t npool = pooled ? (size_t)N * (H / 2) * (W / 2) * Cout : 0;
+  __nv_bfloat16 *d_x = nullptr, *d_y = nullptr, *d_p = nullptr;
+  float* d_f = nullptr;
+  int* d_err = nullptr;
+  std::vector<__nv_bfloat16> hy(nout), hp(npool);
+  ConvLaunch Ln;
+  auto cleanup = [&]() {
+    cudaFree(d_x);
+    cudaFree(d_y);
+    cudaFree(d_p);
+    cudaFree(d_f);
+    cudaFree(d_err);
+    cudaFree(l.d_w);
+    cudaFree(l.d_bias);
+    cudaFree(l.d_skip_s);
+    cudaFree(l.d_skip_t);
+  };
+#define DBG_TRY(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      cleanup();                                                                              \
+      return fail(SCV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                         \
+  } while (0)
+  if (rc != SCV_OK) {
+    cleanup();
+    return rc;
+  }
+  DBG_TRY(cudaMalloc(&d_x, xin.size() * 2));
+  DBG_TRY(cudaMalloc(&d_y, nout * 2));
+  DBG_TRY(cudaMemset(d_y, 0xff, nout * 2));  // NaN pattern: unwritten outputs are visible
+  if (pooled) {
+    DBG_TRY(cudaMalloc(&d_p, npool * 2));
+    DBG_TRY(cudaMemset(d_p, 0xff, npool * 2));
+  }
+  DBG_TRY(cudaMalloc(&d_err, sizeof(int)));
+  DBG_TRY(cudaMemset(d_err, 0, sizeof(int)));
+  DBG_TRY(cudaMemcpy(d_x, xin.data(), xin.size() * 2, cudaMemcpyHostToDevice));
+  rc = fill_launch(nullptr, l, d_x, l.cin_pad, N, H, W, &Ln);
+  if (rc != SCV_OK) {
+    cleanup();
+    return rc;
+  }
+  if (const char* s = getenv("SCV_DEBUG_STAGES")) Ln.p.nstage = std::max(1, atoi(s));
+  Ln.p.relu = relu;
+  Ln.p.out = d_y;
+  Ln.p.out_pitch = Cout;
+  Ln.p.out_choff = 0;
+  Ln.p.pool_out = d_p;
+  Ln.p.pool_pitch = Cout;
+  Ln.p.err = d_err;
+  Ln.smem = conv_smem_bytes(l.KC, l.BN, Ln.p.nstage, l.epi, 1);
+  DBG_TRY(conv_launch(Ln, 0));
+  DBG_TRY(cudaDeviceSynchronize());
+  int herr = 0;
+  DBG_TRY(cudaMemcpy(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  DBG_TRY(cudaMemcpy(hy.data(), d_y, nout * 2, cudaMemcpyDeviceToHost));
+  if (pooled) DBG_TRY(cudaMemcpy(hp.data(), d_p, npool * 2, cudaMemcpyDeviceToHost));
+  cleanup();
+#undef DBG_TRY
+  for (size_t i = 0; i < nout; ++i) y[i] = __bfloat162float(hy[i]);
+  for (size_t i = 0; i < npool; ++i) pooled[i] = __bfloat162float(hp[i]);
+  if (herr) return fail(SCV_ERR_KERNEL, "device watchdog tripped in debug conv (KC=%d BN=%d stages=%d)", l.KC, l.BN, Ln.p.nstage);
+  return SCV_OK;
+}
+
+int scv_debug_conv3x3(int device, const float* x, int N, int H, int W, int Cin, const float* kernel, const float* bias,
+                      int Cout, int relu, float* y, float* pooled) {
+  if (!x || !kernel || !bias || !y) return fail(SCV_ERR_INVALID, "NULL argument");
+  if (pooled && ((H | W) & 1)) return fail(SCV_ERR_INVALID, "pooled output needs even H and W");
+  return debug_conv(device, L_CONV3, x, N, H, W, Cin, kernel, bias, Cout, relu, y, pooled);
+}
+
+int scv_debug_convT2x2(int device, const float* x, int N, int H, int W, int Cin, const float* kernel,
+                       const float* bias, int Cout, int relu, float* y) {
+  if (!x || !kernel || !bias || !y) return fail(SCV_ERR_INVALID, "NULL argument");
+  return debug_conv(device, L_CONVT, x, N, H, W, Cin, kernel, bias, Cout, relu, y, nullptr);
+}
+
+int scv_debug_extract(int device, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
+                      const scv_norm* norm, const int32_t* indices_yx, int n_tiles, float* tiles_out, int* cpad_out) {
+  if (!hwc || !tiling || !indices_yx || !tiles_out) return fail(SCV_ERR_INVALID, "NULL argument");
+  if (dtype_bytes(dtype) == 0) return fail(SCV_ERR_INVALID, "unknown dtype %d", dtype);
+  if (C < 1 || C > SCV_MAX_BANDS) return fail(SCV_ERR_INVALID, "C out of range");
+  SCV_TRY(debug_common_begin(device));
+  const int side = tiling->kernel + tiling->buff, half = tiling->buff / 2;
+  const int cpad = pad_channels(C);
+  if (cpad_out) *cpad_out = cpad;
+  std::vector<int2> org(n_tiles);
+  for (int i = 0; i < n_tiles; ++i) {
+    org[i] = make_int2(indices_yx[2 * i + 1] - half, indices_yx[2 * i] - half);
+    if (org[i].x < 0 || org[i].y < 0 || org[i].x + side > W || org[i].y + side > H)
+      return fail(SCV_ERR_INVALID, "chip %d at (%d,%d) leaves the %dx%d mosaic", i, indices_yx[2 * i], indices_yx[2 * i + 1], H, W);
+  }
+  const size_t src_bytes = (size_t)H * W * C * dtype_bytes(dtype);
+  const size_t nout = (size_t)n_tiles * side * side * cpad;
+  void* d_src = nullptr;
+  int2* d_org = nullptr;
+  __nv_bfloat16* d_out = nullptr;
+  float* d_stats = nullptr;
+  std::vector<__nv_bfloat16> h(nout);
+  auto cleanup = [&]() {
+    cudaFree(d_src);
+    cudaFree(d_org);
+    cudaFree(d_out);
+    cudaFree(d_stats);
+  };
+#define DBG_TRY(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      cleanup();                                                                              \
+      return fail(SCV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    }                                                                                         \
+  } while (0)
+  DBG_TRY(cudaMalloc(&d_src, src_bytes));
+  DBG_TRY(cudaMalloc(&d_org, org.size() * sizeof(int2)));
+  DBG_TRY(cudaMalloc(&d_out, nout * 2));
+  DBG_TRY(cudaMemcpy(d_src, hwc, src_bytes, cudaMemcpyHostToDevice));
+  DBG_TRY(cudaMemcpy(d_org, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  ExtractParams ep{};
+  ep.src = (const uint8_t*)d_src;
+  ep.src_bytes = src_bytes;
+  ep.dtype = dtype;
+  ep.W = W;
+  ep.C = C;
+  ep.src_row0 = 0;
+  ep.origins = d_org;
+  ep.n_tiles = n_tiles;
+  ep.side = side;
+  ep.cpad = cpad;
+  int rc = norm_to_params(norm, C, &ep);
+  if (rc != SCV_OK) {
+    cleanup();
+    return rc;
+  }
+  const int row_bytes = side * C * dtype_bytes(dtype);
+  ep.rows_per_block = std::max(1, std::min(8, (44 * 1024) / (row_bytes + 32)));
+  ep.out = d_out;
+  if (ep.norm_mode == SCV_NORM_TILE_ZSCORE || ep.norm_mode == SCV_NORM_TILE_MINMAX) {
+    DBG_TRY(cudaMalloc(&d_stats, (size_t)n_tiles * C * 2 * sizeof(float)));
+    TileStatsParams sp{};
+    sp.src = ep.src;
+    sp.dtype = dtype;
+    sp.W = W;
+    sp.C = C;
+    sp.src_row0 = 0;
+    sp.origins = d_org;
+    sp.side = side;
+    sp.mode = ep.norm_mode;
+    sp.eps = ep.div[0];
+    sp.stats = d_stats;
+    DBG_TRY(launch_tile_stats(sp, n_tiles, 0));
+    ep.tile_stats = d_stats;
+  }
+  DBG_TRY(launch_extract(ep, 0));
+  DBG_TRY(cudaDeviceSynchronize());
+  DBG_TRY(cudaMemcpy(h.data(), d_out, nout * 2, cudaMemcpyDeviceToHost));
+  cleanup();
+#undef DBG_TRY
+  for (size_t i = 0; i < nout; ++i) tiles_out[i] = __bfloat162float(h[i]);
+  return SCV_OK;
+}
+
+}  // extern "C"

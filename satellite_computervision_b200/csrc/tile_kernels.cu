@@ -1,0 +1,399 @@
+#include "tile_kernels.cuh"
+
+namespace scv {
+
+namespace {
+
+__host__ __device__ inline int dtype_size(int dt) {
+  switch (dt) {
+    case SCV_U8: return 1;
+    case SCV_U16:
+    case SCV_I16: return 2;
+    case SCV_F32: return 4;
+    default: return 8;
+  }
+}
+
+__device__ __forceinline__ float load_elem(const uint8_t* p, int dt) {
+  switch (dt) {
+    case SCV_U8: return static_cast<float>(*p);
+    case SCV_U16: return static_cast<float>(*reinterpret_cast<const uint16_t*>(p));
+    case SCV_I16: return static_cast<float>(*reinterpret_cast<const int16_t*>(p));
+    case SCV_F32: return *reinterpret_cast<const float*>(p);
+    default: return static_cast<float>(*reinterpret_cast<const double*>(p));
+  }
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ int smem_row_stride(int row_bytes) { return (row_bytes + 16 + 15) & ~15; }
+
+// K1.  One block = `rows_per_block` rows of one chip.  Stage: the rows' bytes are
+// fetched with 128-bit loads from the 16-byte-aligned span covering them (any
+// element alignment of the chip origin is handled) into shared memory.  Compute:
+// one thread per pixel reads its C bands from shared memory, normalises in fp32
+// exactly as the reference writes it (subtract, then IEEE divide), and writes
+// cpad bf16 channels with 128-bit stores (a warp writes 32*cpad*2 contiguous bytes).
+__global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int tile = blockIdx.y;
+  const int r0 = blockIdx.x * p.rows_per_block;
+  const int2 org = p.origins[tile];
+  const int esize = dtype_size(p.dtype);
+  const int row_bytes = p.side * p.C * esize;
+  const int sstride = smem_row_stride(row_bytes);
+  const int nrows = min(p.rows_per_block, p.side - r0);
+  const uint8_t* src_end = p.src + p.src_bytes;
+
+  for (int rr = 0; rr < nrows; ++rr) {
+    const long long gofs =
+        (static_cast<long long>(org.y + r0 + rr - p.src_row0) * p.W + org.x) * p.C * esize;
+    const uint8_t* g = p.src + gofs;
+    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
+    const uint8_t* g0 = g - mis;
+    const int nvec = (mis + row_bytes + 15) >> 4;
+    uint8_t* srow = sm + rr * sstride;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const uint8_t* gv = g0 + (v << 4);
+      uint4 val;
+      if (gv >= p.src && gv + 16 <= src_end) {
+        val = __ldg(reinterpret_cast<const uint4*>(gv));
+      } else {
+        uint8_t tmp[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) tmp[b] = (gv + b >= p.src && gv + b < src_end) ? gv[b] : uint8_t(0);
+        val = *reinterpret_cast<uint4*>(tmp);
+      }
+      *reinterpret_cast<uint4*>(srow + (v << 4)) = val;
+    }
+  }
+  __syncthreads();
+
+  const int C = p.C;
+  const int nchunk = p.cpad >> 3;
+  for (int i = threadIdx.x; i < nrows * p.side; i += blockDim.x) {
+    const int rr = i / p.side;
+    const int x = i - rr * p.side;
+    const long long gofs =
+        (static_cast<long long>(org.y + r0 + rr - p.src_row0) * p.W + org.x) * p.C * esize;
+    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(p.src + gofs) & 15);
+    const uint8_t* s = sm + rr * sstride + mis + x * C * esize;
+    float v[SCV_MAX_BANDS];
+#pragma unroll
+    for (int c = 0; c < SCV_MAX_BANDS; ++c) v[c] = (c < C) ? load_elem(s + c * esize, p.dtype) : 0.f;
+
+    if (p.norm_mode == SCV_NORM_PER_BAND) {
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], p.sub[c]), p.div[c]);
+    } else if (p.norm_mode == SCV_NORM_TILE_ZSCORE || p.norm_mode == SCV_NORM_TILE_MINMAX) {
+      const float* st = p.tile_stats + static_cast<size_t>(tile) * C * 2;
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], st[2 * c]), st[2 * c + 1]);
+    } else if (p.norm_mode == SCV_NORM_PIXEL_MINMAX) {
+      float mn = v[0], mx = v[0];
+#pragma unroll
+      for (int c = 1; c < SCV_MAX_BANDS; ++c)
+        if (c < C) {
+          mn = fminf(mn, v[c]);
+          mx = fmaxf(mx, v[c]);
+        }
+      const float den = __fadd_rn(__fsub_rn(mx, mn), p.div[0]);
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mn), den);
+    } else if (p.norm_mode == SCV_NORM_PIXEL_ZSCORE) {
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) sum = __fadd_rn(sum, v[c]);
+      const float mean = __fdiv_rn(sum, static_cast<float>(C));
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) {
+          const float d = __fsub_rn(v[c], mean);
+          ss = __fadd_rn(ss, __fmul_rn(d, d));
+        }
+      const float den = __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, static_cast<float>(C)), p.div[0]));
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mean), den);
+    }
+
+    __nv_bfloat16* o = p.out + ((static_cast<size_t>(tile) * p.side + (r0 + rr)) * p.side + x) * p.cpad;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int k = 0; k < SCV_MAX_BANDS / 8; ++k) {
+      if (k < nchunk) {
+        uint4 w;
+        w.x = pack2(v[8 * k + 0], v[8 * k + 1]);
+        w.y = pack2(v[8 * k + 2], v[8 * k + 3]);
+        w.z = pack2(v[8 * k + 4], v[8 * k + 5]);
+        w.w = pack2(v[8 * k + 6], v[8 * k + 7]);
+        o4[k] = w;
+      }
+    }
+    for (int k = SCV_MAX_BANDS / 8; k < nchunk; ++k) o4[k] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// Per-tile per-band statistics for SCV_NORM_TILE_* (one block per tile).
+// Two passes like tf.nn.moments: mean, then mean of squared differences.
+__global__ void __launch_bounds__(256) tile_stats_kernel(const TileStatsParams p) {
+  __shared__ float red[2][SCV_MAX_BANDS][8];
+  __shared__ float s_mean[SCV_MAX_BANDS];
+  const int tile = blockIdx.x;
+  const int2 org = p.origins[tile];
+  const int esize = dtype_size(p.dtype);
+  const int C = p.C;
+  const int npix = p.side * p.side;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool zs = p.mode == SCV_NORM_TILE_ZSCORE;
+
+  float a[SCV_MAX_BANDS], b[SCV_MAX_BANDS];
+  for (int pass = 0; pass < (zs ? 2 : 1); ++pass) {
+#pragma unroll
+    for (int c = 0; c < SCV_MAX_BANDS; ++c) {
+      a[c] = zs ? 0.f : INFINITY;
+      b[c] = zs ? 0.f : -INFINITY;
+    }
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+      const int y = i / p.side, x = i - y * p.side;
+      const uint8_t* s =
+          p.src + ((static_cast<long long>(org.y + y - p.src_row0) * p.W + org.x + x) * C) * esize;
+#pragma unroll
+      for (int c = 0; c < SCV_MAX_BANDS; ++c)
+        if (c < C) {
+          const float v = load_elem(s + c * esize, p.dtype);
+          if (zs) {
+            if (pass == 0) a[c] += v;
+            else {
+              const float d = v - s_mean[c];
+              a[c] += d * d;
+            }
+          } else {
+            a[c] = fminf(a[c], v);
+            b[c] = fmaxf(b[c], v);
+          }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SCV_MAX_BANDS; ++c) {
+      if (c < C) {
+        for (int o = 16; o > 0; o >>= 1) {
+          const float oa = __shfl_xor_sync(0xffffffffu, a[c], o);
+          const float ob = __shfl_xor_sync(0xffffffffu, b[c], o);
+          a[c] = zs ? a[c] + oa : fminf(a[c], oa);
+          b[c] = zs ? b[c] + ob : fmaxf(b[c], ob);
+        }
+        if (lane == 0) {
+          red[0][c][warp] = a[c];
+          red[1][c][warp] = b[c];
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      const int c = threadIdx.x;
+      float ra = red[0][c][0], rb = red[1][c][0];
+      for (int w = 1; w < 8; ++w) {
+        ra = zs ? ra + red[0][c][w] : fminf(ra, red[0][c][w]);
+        rb = zs ? rb + red[1][c][w] : fmaxf(rb, red[1][c][w]);
+      }
+      float* st = p.stats + (static_cast<size_t>(tile) * C + c) * 2;
+      if (zs) {
+        if (pass == 0) s_mean[c] = ra / static_cast<float>(npix);
+        else {
+          st[0] = s_mean[c];
+          st[1] = sqrtf(ra / static_cast<float>(npix) + p.eps);
+        }
+      } else {
+        st[0] = ra;
+        st[1] = (rb - ra) + p.eps;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void head_eval(const float* z, int ncls, int head, float thr, int out_channel,
+                                          float& prob, int& cls) {
+  if (head == SCV_HEAD_SIGMOID) {
+    const float pr = 1.f / (1.f + expf(-z[0]));
+    prob = pr;
+    cls = pr > thr ? 1 : 0;
+  } else {
+    float m = z[0];
+    for (int k = 1; k < ncls; ++k) m = fmaxf(m, z[k]);
+    float e[SCV_MAX_CLASSES];
+    float sum = 0.f;
+    for (int k = 0; k < ncls; ++k) {
+      e[k] = expf(z[k] - m);
+      sum += e[k];
+    }
+    float best = -1.f;
+    int bi = 0;
+    for (int k = 0; k < ncls; ++k) {
+      const float pk = e[k] / sum;
+      if (pk > best) {
+        best = pk;
+        bi = k;
+      }
+      if (k == out_channel) prob = pk;
+    }
+    cls = bi;
+  }
+}
+
+// K4, vector path: sigmoid head (ncls == 1), 4 consecutive core pixels per thread,
+// float4 logit load, float4 probability store, 32-bit mask store.
+__global__ void __launch_bounds__(256) stitch_kernel_vec4(const StitchParams p) {
+  const int tile = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = p.kernel >> 2;
+  if (q >= per_row * p.kernel) return;
+  const int row = q / per_row;
+  const int col = (q - row * per_row) << 2;
+  const int2 d = p.dst_origins[tile];
+  const float4 z = __ldg(reinterpret_cast<const float4*>(
+      p.logits + (static_cast<size_t>(tile) * p.side + (p.crop + row)) * p.side + p.crop + col));
+  float4 pr;
+  pr.x = 1.f / (1.f + expf(-z.x));
+  pr.y = 1.f / (1.f + expf(-z.y));
+  pr.z = 1.f / (1.f + expf(-z.z));
+  pr.w = 1.f / (1.f + expf(-z.w));
+  const size_t o = static_cast<size_t>(d.y + row - p.dst_row0) * p.out_W + d.x + col;
+  if (p.prob) *reinterpret_cast<float4*>(p.prob + o) = pr;
+  if (p.mask) {
+    const uint32_t m = (pr.x > p.threshold ? 1u : 0u) | (pr.y > p.threshold ? 1u << 8 : 0u) |
+                       (pr.z > p.threshold ? 1u << 16 : 0u) | (pr.w > p.threshold ? 1u << 24 : 0u);
+    *reinterpret_cast<uint32_t*>(p.mask + o) = m;
+  }
+}
+
+// K4, general path: any head / class count / alignment, one pixel per thread.
+__global__ void __launch_bounds__(256) stitch_kernel_scalar(const StitchParams p) {
+  const int tile = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.kernel * p.kernel) return;
+  const int row = q / p.kernel;
+  const int col = q - row * p.kernel;
+  const int2 d = p.dst_origins[tile];
+  const float* z =
+      p.logits + ((static_cast<size_t>(tile) * p.side + (p.crop + row)) * p.side + p.crop + col) * p.ncls;
+  float zz[SCV_MAX_CLASSES];
+  for (int k = 0; k < p.ncls; ++k) zz[k] = __ldg(z + k);
+  float prob = 0.f;
+  int cls = 0;
+  head_eval(zz, p.ncls, p.head, p.threshold, p.out_channel, prob, cls);
+  const size_t o = static_cast<size_t>(d.y + row - p.dst_row0) * p.out_W + d.x + col;
+  if (p.prob) p.prob[o] = prob;
+  if (p.mask) p.mask[o] = static_cast<uint8_t>(cls);
+}
+
+__global__ void __launch_bounds__(256) head_tiles_kernel(const HeadTilesParams p) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= p.npix) return;
+  float zz[SCV_MAX_CLASSES];
+  for (int k = 0; k < p.ncls; ++k) zz[k] = __ldg(p.logits + i * p.ncls + k);
+  if (p.head == SCV_HEAD_SIGMOID) {
+    const float pr = 1.f / (1.f + expf(-zz[0]));
+    if (p.probs) p.probs[i] = pr;
+    if (p.classes) p.classes[i] = pr > p.threshold ? 1 : 0;
+  } else {
+    float m = zz[0];
+    for (int k = 1; k < p.ncls; ++k) m = fmaxf(m, zz[k]);
+    float sum = 0.f;
+    for (int k = 0; k < p.ncls; ++k) {
+      zz[k] = expf(zz[k] - m);
+      sum += zz[k];
+    }
+    float best = -1.f;
+    int bi = 0;
+    for (int k = 0; k < p.ncls; ++k) {
+      const float pk = zz[k] / sum;
+      if (p.probs) p.probs[i * p.ncls + k] = pk;
+      if (pk > best) {
+        best = pk;
+        bi = k;
+      }
+    }
+    if (p.classes) p.classes[i] = bi;
+  }
+}
+
+__global__ void widen_kernel(const __nv_bfloat16* src, float* dst, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+__global__ void narrow_kernel(const float* src, __nv_bfloat16* dst, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace
+
+size_t extract_smem_bytes(const ExtractParams& p) {
+  const int row_bytes = p.side * p.C * dtype_size(p.dtype);
+  return static_cast<size_t>(p.rows_per_block) * ((row_bytes + 16 + 15) & ~15);
+}
+
+cudaError_t launch_extract(const ExtractParams& p, cudaStream_t s) {
+  if (p.n_tiles <= 0) return cudaSuccess;
+  const size_t smem = extract_smem_bytes(p);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid((p.side + p.rows_per_block - 1) / p.rows_per_block, p.n_tiles);
+  extract_kernel<<<grid, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile_stats(const TileStatsParams& p, int n_tiles, cudaStream_t s) {
+  if (n_tiles <= 0) return cudaSuccess;
+  tile_stats_kernel<<<n_tiles, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stitch(const StitchParams& p, int n_tiles, cudaStream_t s) {
+  if (n_tiles <= 0) return cudaSuccess;
+  const bool vec = p.head == SCV_HEAD_SIGMOID && p.ncls == 1 && (p.kernel & 3) == 0 && (p.crop & 3) == 0 &&
+                   (p.side & 3) == 0 && (p.out_W & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.prob) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0;
+  if (vec && !p.force_scalar) {
+    dim3 grid(((p.kernel >> 2) * p.kernel + 255) / 256, n_tiles);
+    stitch_kernel_vec4<<<grid, 256, 0, s>>>(p);
+  } else {
+    dim3 grid((p.kernel * p.kernel + 255) / 256, n_tiles);
+    stitch_kernel_scalar<<<grid, 256, 0, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_tiles(const HeadTilesParams& p, cudaStream_t s) {
+  if (p.npix <= 0) return cudaSuccess;
+  head_tiles_kernel<<<static_cast<unsigned>((p.npix + 255) / 256), 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_widen(const __nv_bfloat16* src, float* dst, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  widen_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_narrow(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  narrow_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+}  // namespace scv

@@ -1,0 +1,143 @@
+"""GPU parity of the individual kernels through the C-ABI debug entry points:
+UMMA implicit-GEMM conv / convT against a torch fp32 reference of the same op
+(bf16 operands, fp32 accumulate: tolerance = 1 bf16 ulp of the result + 2e-3), and
+the extract kernel bit-exactly against the oracle normalisers."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import normalize as onorm
+from oracle import tiling as otile
+from satellite_computervision_b200 import _lib, processing
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout            exercised path
+    (2, 32, 32, 6, 32),           # KC=16 (6->16 pad), SW32, BN=32, box 16x8x1
+    (1, 16, 48, 3, 64),           # KC=16, BN=64
+    (2, 32, 32, 32, 32),          # KC=32, SW64
+    (1, 32, 32, 32, 64),          # KC=32, BN=64
+    (2, 16, 32, 64, 32),          # KC=64, SW128, BN=32
+    (1, 32, 32, 64, 64),
+    (1, 16, 32, 64, 128),         # BN=128
+    (1, 16, 16, 128, 128),        # 2 channel chunks per tap
+    (1, 16, 16, 128, 256),        # BN=256
+    (1, 8, 16, 256, 512),         # 2 N tiles
+    (3, 24, 24, 64, 64),          # box 8x8x2, odd N -> OOB image in the last tile
+    (5, 12, 12, 128, 256),        # box 4x4x8, N tail
+    (1, 20, 20, 32, 32),          # partial tiles in x and y (masked stores)
+    (1, 40, 72, 64, 32),          # non-square
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', CONV_CASES)
+def test_conv3x3_matches_torch(N, H, W, Cin, Cout):
+    rng = np.random.default_rng(N * 1000 + H + W + Cin + Cout)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    got = G.conv3x3_device(x, k, b)
+    ref = G.conv3x3_ref(x, k, b)
+    s = G.err_stats(got, ref)
+    print('conv3x3', (N, H, W, Cin, Cout), s)
+    assert s['nan'] == 0 and s['n_bad'] == 0, s
+
+
+def test_conv3x3_without_relu_keeps_negatives():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1, 16, 16, 32)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, 32, 32)) / 17).astype(np.float32)
+    b = np.zeros(32, np.float32)
+    got = G.conv3x3_device(x, k, b, relu=False)
+    s = G.err_stats(got, G.conv3x3_ref(x, k, b, relu=False))
+    assert s['n_bad'] == 0 and (got < 0).mean() > 0.3
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 32, 32, 32, 32), (2, 24, 24, 64, 64), (8, 4, 4, 64, 32), (1, 16, 48, 6, 32)])
+def test_fused_maxpool_epilogue(N, H, W, Cin, Cout):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    y, p = G.conv3x3_device(x, k, b, pooled=True)
+    ref = G.conv3x3_ref(x, k, b)
+    assert G.err_stats(y, ref)['n_bad'] == 0
+    # the pooled tensor must be exactly the 2x2 max of the full-resolution output the same kernel wrote
+    assert np.array_equal(p, G.maxpool_ref(y))
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(1, 16, 16, 64, 32), (2, 12, 12, 128, 64), (2, 6, 6, 1024, 512), (1, 8, 24, 256, 128)])
+def test_convT2x2_matches_torch(N, H, W, Cin, Cout):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((2, 2, Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    got = G.convT_device(x, k, b)
+    s = G.err_stats(got, G.convT_ref(x, k, b))
+    print('convT', (N, H, W, Cin, Cout), s)
+    assert s['nan'] == 0 and s['n_bad'] == 0, s
+
+
+def _extract(hwc, tiling, norm, indices):
+    lib = _lib.load_library()
+    a, dt = _lib.as_input(hwc)
+    H, W, Cc = a.shape
+    t = _lib.Tiling(*tiling)
+    side = tiling[0] + tiling[1]
+    idx = np.ascontiguousarray(np.array(indices, dtype=np.int32).reshape(-1, 2))
+    out = np.empty((len(idx), side, side, 16), np.float32)
+    cpad = C.c_int()
+    _lib.check(lib.scv_debug_extract(0, _lib.ptr(a), dt, H, W, Cc, C.byref(t), C.byref(norm.to_c(Cc)), _lib.ptr(idx),
+                                     len(idx), _lib.ptr(out), C.byref(cpad)))
+    assert cpad.value == 16
+    return out
+
+
+@pytest.mark.parametrize('dtype', ['uint16', 'float32', 'float64', 'uint8', 'int16'])
+def test_extract_per_band_bit_exact(dtype):
+    """Chip placement bit-exact and values == bf16(reference float32 normaliser output)."""
+    rng = np.random.default_rng(3)
+    H, W, Cc = 300, 333, 6  # odd width: rows start at every 16-byte misalignment
+    if dtype == 'uint16':
+        arr = rng.integers(0, 10000, (H, W, Cc), dtype=np.uint16)
+    elif dtype == 'uint8':
+        arr = rng.integers(0, 255, (H, W, Cc), dtype=np.uint8)
+    elif dtype == 'int16':
+        arr = rng.integers(-2000, 10000, (H, W, Cc)).astype(np.int16)
+    else:
+        arr = (rng.random((H, W, Cc)) * 10000).astype(dtype)
+    kernel, buff = 64, 32
+    idx = otile.generate_chip_indices(arr.shape, buff, kernel)
+    assert len(idx) == 12
+    mm = [(0, 10000), (10.0, 9000.0), (0.0, 8000.5), (1.0, 3000.0), (0.0, 10000.0), (200.0, 7000.0)]
+    spec = processing.rescale_spec(Cc, moments=mm)
+    got = _extract(arr, (kernel, buff), spec, idx)
+    for i, (y, x) in enumerate(idx):
+        chip = arr[y - 16:y + 80, x - 16:x + 80, :]
+        want = G.bf16_round(onorm.rescale_tensor(chip.astype(np.float32), moments=mm))
+        assert np.array_equal(got[i, :, :, :Cc], want), (dtype, i)
+        assert np.all(got[i, :, :, Cc:] == 0)
+
+
+def test_extract_pixel_and_tile_modes():
+    rng = np.random.default_rng(4)
+    arr = (rng.random((200, 216, 6)) * 5000 + 100).astype(np.float32)
+    kernel, buff = 64, 32
+    idx = otile.generate_chip_indices(arr.shape, buff, kernel)
+    chips = [arr[y - 16:y + 80, x - 16:x + 80, :] for y, x in idx]
+    got = _extract(arr, (kernel, buff), processing.rescale_spec(6), idx)  # reference default axes=[2]
+    for i, c in enumerate(chips):
+        assert np.array_equal(got[i, ..., :6], G.bf16_round(onorm.rescale_tensor(c)))
+    got = _extract(arr, (kernel, buff), processing.normalize_spec(6), idx)
+    for i, c in enumerate(chips):
+        np.testing.assert_allclose(got[i, ..., :6], onorm.normalize_tensor(c), rtol=2 ** -7, atol=1e-5)
+    got = _extract(arr, (kernel, buff), processing.normalize_spec(6, axes=[0, 1]), idx)  # solar notebook form
+    for i, c in enumerate(chips):
+        np.testing.assert_allclose(got[i, ..., :6], onorm.normalize_tensor(c, axes=(0, 1)), rtol=2 ** -7, atol=2e-3)
+    got = _extract(arr, (kernel, buff), processing.rescale_spec(6, axes=[0, 1]), idx)
+    for i, c in enumerate(chips):
+        np.testing.assert_allclose(got[i, ..., :6], onorm.rescale_tensor(c, axes=(0, 1)), rtol=2 ** -7, atol=1e-5)

@@ -1,0 +1,138 @@
+"""GPU parity of the whole predict path through the public API / C-ABI against the
+CPU oracle (oracle/): probabilities max-abs <= 1e-2, mask agreement >= 99.9 %,
+tile placement / crop / mosaic indexing bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import normalize as onorm
+from oracle import tiling as otile
+from oracle import unet as ounet
+from satellite_computervision_b200 import model_tools, prediction_tools as pt, processing
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-2       # north_star: bf16 compute, fp32 accumulate
+MASK_AGREE = 0.999
+
+
+def _mk(variant, nch, ncls, filters, seed=0, head_bias=None, **kw):
+    specs = ounet.weight_specs(variant, nch, ncls, tuple(filters))
+    w = ounet.init_weights(specs, seed=seed, randomize_bn=True, head_bias=head_bias)
+    if variant == 'A':
+        m = model_tools.binary_unet(nchannels=nch, filters=list(filters), **kw)
+    else:
+        m = model_tools.get_unet_model(ncls, nch, filters=list(filters), factors=[2] * len(filters), **kw)
+    m.set_weights(w)
+    return m, w
+
+
+@pytest.mark.parametrize('variant,ncls,filters,hw,N', [
+    ('A', 1, (32, 64), 64, 3),
+    ('B', 2, (32, 64), 64, 2),
+    ('A', 1, (32, 64, 128), 96, 2),
+    ('B', 3, (32, 64, 128, 256, 512), 96, 5),   # deep levels at 6x6 and 3x3: partial boxes
+])
+def test_small_models_match_oracle(variant, ncls, filters, hw, N):
+    m, w = _mk(variant, 6, ncls, filters, seed=1, outputs='both') if variant == 'A' else _mk(variant, 6, ncls, filters, seed=1)
+    x = np.random.default_rng(2).random((N, hw, hw, 6)).astype(np.float32)
+    head = 'sigmoid' if variant == 'A' else 'softmax'
+    ref_p, ref_c = ounet.forward(x, w, variant, tuple(filters), head=head)
+    probs, classes = m.predict(x)
+    assert probs.shape == ref_p.shape and classes.shape == ref_c.shape and classes.dtype == np.int32
+    err = np.abs(probs - ref_p).max()
+    agree = (classes == ref_c).mean()
+    print(variant, filters, 'max|dp|', err, 'class agreement', agree)
+    assert err <= PROB_TOL
+    assert agree >= MASK_AGREE
+
+
+def test_full_size_tile_variant_a_matches_oracle():
+    """One 384x384x6 Sentinel-2-like tile through the BASELINE network (31 M parameters)."""
+    m, w = _mk('A', 6, 1, ounet.DEFAULT_FILTERS, seed=0, head_bias=0.0, outputs='both')
+    rng = np.random.default_rng(0)
+    dn = rng.integers(0, 10000, (2, 384, 384, 6), dtype=np.uint16)
+    mm = [(0, 10000)] * 6
+    x = np.stack([onorm.rescale_tensor(t.astype(np.float32), moments=mm) for t in dn])
+    ref_p, ref_c = ounet.forward(x, w, 'A')
+    probs, classes = m.predict(dn, norm=processing.rescale_spec(6, moments=mm))
+    d = np.abs(probs - ref_p)
+    near = (np.abs(ref_p - 0.5) < 1e-2).mean()
+    agree = (classes == ref_c).mean()
+    print('full tile: max|dp|', d.max(), 'mean|dp|', d.mean(), 'agree', agree, 'frac within 1e-2 of thr', near,
+          'p range', ref_p.min(), ref_p.max())
+    assert d.max() <= PROB_TOL
+    assert agree >= MASK_AGREE
+
+
+def test_predict_chips_placement_is_bit_exact():
+    """Mosaic path (device gather + stitch) == the reference loop of predict_chips run tile by tile
+    through the same engine: same values, same places, zeros elsewhere."""
+    m, w = _mk('A', 6, 1, (32, 64), seed=3)
+    rng = np.random.default_rng(1)
+    H, W, kernel, buff = 500, 613, 64, 32
+    arr = rng.integers(0, 10000, (H, W, 6), dtype=np.uint16)
+    spec = processing.scalar_spec(6, 10000.0)
+    idx = pt.generate_chip_indices(arr, buff, kernel)
+    assert idx == otile.generate_chip_indices(arr.shape, buff, kernel) and len(idx) == 6 * 8
+    got = pt.predict_chips(arr, idx, np.zeros((H, W)), m, kernel, buff, norm=spec)
+    want = otile.predict_chips(arr, idx, np.zeros((H, W)), lambda b: m.predict(b, norm=spec), kernel, buff)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    assert np.all(got[:16] == 0) and np.all(got[:, :16] == 0) and np.all(got[16 + 6 * 64:] == 0)
+    # subset / repeated indices take the batched-tiles path and accumulate with +=
+    sub = idx[3:11] + idx[3:5]
+    got2 = pt.predict_chips(arr, sub, np.full((H, W), 0.25), m, kernel, buff, norm=spec)
+    want2 = otile.predict_chips(arr, sub, np.full((H, W), 0.25), lambda b: m.predict(b, norm=spec), kernel, buff)
+    assert np.array_equal(got2, want2)
+    # and against the fp32 oracle network: tolerance on values
+    ref = otile.predict_chips(arr.astype(np.float32) / np.float32(10000.0), idx, np.zeros((H, W)),
+                              ounet.make_predict_fn(w, variant='A', filters=(32, 64)), kernel, buff)
+    assert np.abs(got - ref).max() <= PROB_TOL
+
+
+def test_mask_and_tile_row_sharding():
+    m, w = _mk('A', 6, 1, (32, 64), seed=4)
+    rng = np.random.default_rng(2)
+    arr = (rng.random((400, 400, 6)) * 10000).astype(np.float32)
+    spec = processing.scalar_spec(6, 10000.0)
+    prob, mask = m.predict_mosaic(arr, buff=32, kernel=64, norm=spec)
+    assert np.array_equal(mask, (prob > 0.5).astype(np.uint8))
+    # two row bands written into the same rasters == one call (multi-GPU sharding contract)
+    p2 = np.zeros_like(prob)
+    k2 = np.zeros_like(mask)
+    m.predict_mosaic(arr, buff=32, kernel=64, norm=spec, tile_rows=(0, 2), out_prob=p2, out_mask=k2)
+    assert np.all(p2[16 + 128:] == 0)
+    m.predict_mosaic(arr, buff=32, kernel=64, norm=spec, tile_rows=(2, -1), out_prob=p2, out_mask=k2)
+    assert np.array_equal(p2, prob) and np.array_equal(k2, mask)
+
+
+def test_patch_list_geometry_matches_oracle():
+    m, w = _mk('B', 6, 2, (32, 64), seed=5)
+    rng = np.random.default_rng(3)
+    cols, rows, k, b = 3, 2, 64, 32
+    patches = rng.random((cols * rows, k + b, k + b, 6)).astype(np.float32)
+    mixer = {'patchesPerRow': cols, 'totalPatches': cols * rows, 'patchDimensions': [k, k]}
+    preds = m.predict(patches)
+    want = otile.make_array_predictions([preds[0], preds[1]], mixer, [k, k], [b, b])
+    got = pt.make_array_predictions([p[None] for p in patches], m, mixer, [k, k], [b, b])
+    assert np.array_equal(got, want)
+    assert np.array_equal(pt.callback_predictions(patches, m, mixer, [k, k], [b, b]),
+                          otile.callback_predictions(preds, mixer, [k, k], [b, b]))
+    gt, _, _ = pt.geotiff_predictions(patches, m, mixer, [b, b])
+    assert np.array_equal(gt, otile.geotiff_stitch(preds, mixer, [b, b]))
+
+
+def test_overlap_chunk_geometry_matches_oracle():
+    m, w = _mk('A', 6, 1, (32, 64), seed=6)
+    chw = np.random.default_rng(4).random((6, 128, 192)).astype(np.float32)
+    got = pt.predict_overlap_chunks(chw, m, chunk=64, depth=16)
+    want = otile.predict_overlap_chunks(chw, lambda b: m.predict(b), chunk=64, depth=16)
+    assert np.array_equal(got, want)
+
+
+def test_errors_are_loud():
+    m, _ = _mk('A', 6, 1, (32, 64), seed=0)
+    with pytest.raises(ValueError):
+        m.predict(np.zeros((1, 50, 50, 6), np.float32))      # not a multiple of 2^levels
+    with pytest.raises(ValueError):
+        m.predict(np.zeros((1, 64, 64, 5), np.float32))      # wrong band count
+    assert pt.predict_chips(np.zeros((96, 96, 6), np.float32), [], np.zeros((96, 96)), m, 64, 32).sum() == 0
