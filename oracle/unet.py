@@ -79,12 +79,15 @@ def weight_specs(variant='A', nchannels=6, nclasses=1, filters=DEFAULT_FILTERS):
     return specs
 
 
-def init_weights(specs, seed=0, randomize_bn=True, head_bias=None, dtype=np.float32):
+def init_weights(specs, seed=0, randomize_bn=True, head_bias=None, head_gain=1.0, dtype=np.float32):
     """Deterministic Keras-style weights: glorot-uniform kernels, zero biases.
 
     ``randomize_bn`` draws gamma~U(0.5,1.5), beta~N(0,0.1), mean~N(0,0.1),
     var~U(0.5,1.5) and small random conv biases so BN folding is exercised;
-    otherwise BN is the Keras default (1, 0, 0, 1).
+    otherwise BN is the Keras default (1, 0, 0, 1).  ``head_gain`` scales the 1x1 head
+    kernel: with a plain glorot head every probability of a random-init net sits within
+    ~1e-2 of 0.5 (hard part 1), which makes thresholded-mask agreement a
+    coin-flip test of rounding noise; a gain spreads the logits the way training does.
     """
     rng = np.random.default_rng(seed)
     out = []
@@ -99,6 +102,8 @@ def init_weights(specs, seed=0, randomize_bn=True, head_bias=None, dtype=np.floa
                 fan_in, fan_out = kh * kw * ci, kh * kw * co
             limit = np.sqrt(6.0 / (fan_in + fan_out))
             w = rng.uniform(-limit, limit, shape)
+            if name.startswith('head'):
+                w = w * head_gain
         elif leaf == 'bias':
             if name.startswith('head') and head_bias is not None:
                 w = np.full(shape, head_bias, dtype=np.float64)

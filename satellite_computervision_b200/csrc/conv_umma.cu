@@ -1,4 +1,4 @@
-// Instantiations + dispatch of the UMMA implicit-GEMM convolution kernel.
+// Instantiations + dispatch of the UMMA implicit-GEMM convolution kernels.
 #include "conv_umma.cuh"
 
 namespace scv {
@@ -6,12 +6,30 @@ namespace scv {
 namespace {
 template <int KC, int BN, int EPI>
 cudaError_t launch_one(const ConvLaunch& L, cudaStream_t stream) {
-  conv_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  if (L.slab) {
+    constexpr int NT = slab_threads(BN, EPI);
+    if constexpr (EPI == EPI_CONVT) {
+      conv_slab_kernel<KC, BN, EPI, 1><<<L.grid, NT, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+    } else {
+      if (L.p.ntaps == 9)
+        conv_slab_kernel<KC, BN, EPI, 9><<<L.grid, NT, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+      else
+        return cudaErrorInvalidValue;
+    }
+  } else {
+    conv_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  }
   return cudaGetLastError();
 }
 template <int KC, int BN, int EPI>
 cudaError_t attr_one() {
-  return cudaFuncSetAttribute(conv_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const int kMax = 227 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+  if (e != cudaSuccess) return e;
+  if constexpr (EPI == EPI_CONVT)
+    return cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+  else
+    return cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 
 template <int KC, int BN>
@@ -69,10 +87,13 @@ cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
 }
 
 cudaError_t conv_init_attributes() {
+  static bool done = false;
+  if (done) return cudaSuccess;
   cudaError_t e;
   if ((e = attr_bn<16>()) != cudaSuccess) return e;
   if ((e = attr_bn<32>()) != cudaSuccess) return e;
   if ((e = attr_bn<64>()) != cudaSuccess) return e;
+  done = true;
   return cudaSuccess;
 }
 

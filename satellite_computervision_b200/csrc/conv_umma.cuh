@@ -7,10 +7,16 @@
 // :281-286 (MaxPooling2D), :306-309 (Conv2DTranspose -> concatenate -> BN -> ReLU)
 // and :405 / :443 (1x1 head conv; activation happens in the stitch kernel).
 //
-// GEMM view: M = pixels (128 per CTA: a TW x TH x TN box of the NHWC activation
-// tensor, fetched by one 4-D TMA per (tap, channel chunk) with out-of-bounds zero
-// fill supplying the per-tile 'same' padding), N = output channels (BN per CTA),
-// K = taps * Cin walked as (tap, chunk of KC channels).
+// GEMM view: M = pixels (128 per accumulator tile), N = output channels (BN per CTA),
+// K = Cin * taps walked as (channel chunk of KC, tap, 16-wide k step) -- the same order in
+// both kernels below, so a pixel's result does not depend on which kernel (or batch size)
+// produced it.
+//
+//   conv_umma_kernel  one 128 x BN output tile per CTA; the A tile (a TW x TH x TN box of the
+//                     NHWC activation tensor) is fetched by one 4-D TMA per (chunk, tap) with
+//                     out-of-bounds zero fill supplying the per-tile 'same' padding.  Used for the
+//                     deep layers (large Cin*Cout, few pixels).
+//   conv_slab_kernel  persistent + weight-stationary, for the high-resolution layers (see below).
 #pragma once
 #include "ptx.cuh"
 
@@ -42,6 +48,9 @@ struct ConvParams {
   const float* head_b;  // [ncls]
   int ncls;
   float* logits;        // N*H*W*ncls fp32
+  // persistent slab kernel
+  int nslab;            // slab ring depth
+  int num_m_tiles;      // tiles_x * tiles_y * N
   // watchdog
   int* err;
   unsigned long long watchdog_ns;
@@ -64,20 +73,139 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&v)[16]) {
-  uint4 lo, hi;
-  lo.x = pack_bf16x2(v[0], v[1]);
-  lo.y = pack_bf16x2(v[2], v[3]);
-  lo.z = pack_bf16x2(v[4], v[5]);
-  lo.w = pack_bf16x2(v[6], v[7]);
-  hi.x = pack_bf16x2(v[8], v[9]);
-  hi.y = pack_bf16x2(v[10], v[11]);
-  hi.z = pack_bf16x2(v[12], v[13]);
-  hi.w = pack_bf16x2(v[14], v[15]);
-  uint4* p = reinterpret_cast<uint4*>(dst);
-  p[0] = lo;
-  p[1] = hi;
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
 }
+__device__ __forceinline__ void pack16(const float (&v)[16], uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void store_pk16(__nv_bfloat16* dst, const uint32_t (&pk)[8]) {
+  uint4* p = reinterpret_cast<uint4*>(dst);
+  p[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  p[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+__device__ __forceinline__ void lds16(const float* src, float (&dst)[16]) {  // 16-byte aligned smem -> 4 x LDS.128
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = s4[j];
+    dst[4 * j + 0] = t.x;
+    dst[4 * j + 1] = t.y;
+    dst[4 * j + 2] = t.z;
+    dst[4 * j + 3] = t.w;
+  }
+}
+
+// Epilogue of one 128-pixel accumulator tile: this thread owns TMEM lane == pixel (x, y, n).
+// `pair_w` is the lane distance of the vertical 2x2-pool partner (the M-tile's width in pixels).
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int xx, int yy, int x, int y,
+                                              int n, bool valid, int pair_w, int nb0, const float* s_bias,
+                                              const float* s_extra) {
+  const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+  float hacc[kMaxHeadClasses];
+  if constexpr (EPI == EPI_HEAD) {
+#pragma unroll
+    for (int k = 0; k < kMaxHeadClasses; ++k) hacc[k] = 0.f;
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 16) {
+    uint32_t raw[16];
+    tmem_ld16(taddr + c, raw);
+    tmem_ld_wait();
+    float v[16], cst[16];
+    lds16(s_bias + c, cst);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = __uint_as_float(raw[j]) + cst[j];
+      if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if constexpr (EPI == EPI_STORE) {
+      uint32_t pk[8];
+      pack16(v, pk);
+      if (valid) store_pk16(p.out + pix * p.out_pitch + p.out_choff + nb0 + c, pk);
+    } else if constexpr (EPI == EPI_POOL_SKIP) {
+      // 2x2 max-pool on the bf16-rounded values (rounding is monotonic, so max commutes with it)
+      uint32_t pk[8], m[8];
+      pack16(v, pk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t t = max_bf16x2(pk[j], __shfl_xor_sync(0xffffffffu, pk[j], 1));
+        m[j] = max_bf16x2(t, __shfl_xor_sync(0xffffffffu, t, pair_w));
+      }
+      if (valid && !(xx & 1) && !(yy & 1)) {
+        const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+        store_pk16(p.pool_out + ppix * p.pool_pitch + nb0 + c, m);
+      }
+      if (p.out != nullptr) {
+        float sh[16];
+        lds16(s_extra + c, cst);
+        lds16(s_extra + BN + c, sh);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], cst[j], sh[j]), 0.f);
+        pack16(v, pk);
+        if (valid) store_pk16(p.out + pix * p.out_pitch + p.out_choff + nb0 + c, pk);
+      }
+    } else if constexpr (EPI == EPI_CONVT) {
+      const int col = nb0 + c;
+      const int g = col / p.Cout;
+      const int o = col - g * p.Cout;
+      const size_t opix =
+          (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (g >> 1))) * (2 * p.W) + (2 * x + (g & 1));
+      uint32_t pk[8];
+      pack16(v, pk);
+      if (valid) store_pk16(p.out + opix * p.out_pitch + p.out_choff + o, pk);
+    } else {  // EPI_HEAD
+      if (p.ncls == 1) {  // sigmoid head: one dot product per pixel
+        lds16(s_extra + c, cst);
+        float a = hacc[0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a = fmaf(v[j], cst[j], a);
+        hacc[0] = a;
+      } else
+#pragma unroll
+      for (int k = 0; k < kMaxHeadClasses; ++k) {
+        if (k < p.ncls) {
+          float a = hacc[k];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a = fmaf(v[j], s_extra[(c + j) * p.ncls + k], a);
+          hacc[k] = a;
+        }
+      }
+    }
+  }
+  if constexpr (EPI == EPI_HEAD) {
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < kMaxHeadClasses; ++k)
+        if (k < p.ncls) p.logits[pix * p.ncls + k] = hacc[k] + s_extra[BN * p.ncls + k];
+    }
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void load_epilogue_consts(const ConvParams& p, int t, int nthreads, int nb0, float* s_bias,
+                                                     float* s_extra) {
+  for (int i = t; i < BN; i += nthreads) s_bias[i] = p.bias[nb0 + i];
+  if constexpr (EPI == EPI_POOL_SKIP) {
+    for (int i = t; i < BN; i += nthreads) {
+      s_extra[i] = p.skip_s[nb0 + i];
+      s_extra[BN + i] = p.skip_t[nb0 + i];
+    }
+  }
+  if constexpr (EPI == EPI_HEAD) {
+    for (int i = t; i < BN * p.ncls; i += nthreads) s_extra[i] = p.head_w[i];
+    for (int i = t; i < p.ncls; i += nthreads) s_extra[BN * p.ncls + i] = p.head_b[i];
+  }
+}
+
+// NOTE on the producer / MMA warps: the loops run warp-uniformly on all 32 lanes and only the
+// instruction issue is predicated on elect.sync.  Guarding the whole loop with `lane == 0` makes
+// every UTCHMMA / UTMALDG operand "divergent" for the compiler, which then wraps each issue in a
+// ~30-instruction R2UR waterfall loop -- more cycles than a 128x32x16 MMA itself takes.
 
 template <int KC, int BN, int EPI>
 __global__ void __launch_bounds__(kConvThreads)
@@ -97,7 +225,7 @@ __global__ void __launch_bounds__(kConvThreads)
   uint64_t* tmem_full_bar = empty_bar + nstage;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
   float* s_extra = s_bias + BN;  // skip (s,t) or head (w,b)
 
   const int warp = threadIdx.x >> 5;
@@ -135,70 +263,62 @@ __global__ void __launch_bounds__(kConvThreads)
     tmem_alloc(tmem_slot, BN);
     tmem_relinquish();
   }
-  if (warp >= 2) {
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < BN; i += 128) s_bias[i] = p.bias[nb0 + i];
-    if constexpr (EPI == EPI_POOL_SKIP) {
-      for (int i = t; i < BN; i += 128) {
-        s_extra[i] = p.skip_s[nb0 + i];
-        s_extra[BN + i] = p.skip_t[nb0 + i];
-      }
-    }
-    if constexpr (EPI == EPI_HEAD) {
-      for (int i = t; i < BN * p.ncls; i += 128) s_extra[i] = p.head_w[i];
-      for (int i = t; i < p.ncls; i += 128) s_extra[BN * p.ncls + i] = p.head_b[i];
-    }
-  }
+  if (warp >= 2) load_epilogue_consts<BN, EPI>(p, threadIdx.x - 64, 128, nb0, s_bias, s_extra);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % nstage;
-        const uint32_t round = static_cast<uint32_t>(it / nstage);
-        if (!mbar_wait(&empty_bar[s], (round & 1) ^ 1, abort_flag, p.watchdog_ns)) break;
-        const int tap = it / chunks;
-        const int c0 = (it - tap * chunks) * KC;
-        int dy = 0, dx = 0;
-        if (p.ntaps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-        }
-        uint8_t* a_dst = tiles + static_cast<size_t>(s) * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
+    // ===================== TMA producer (warp-uniform loop, elected issue) =====================
+    int ch = 0, tap = 0;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % nstage;
+      const uint32_t round = static_cast<uint32_t>(it / nstage);
+      const bool ok = mbar_wait(&empty_bar[s], (round & 1) ^ 1, abort_flag, p.watchdog_ns);
+      if (!__all_sync(0xffffffffu, ok)) break;
+      int dy = 0, dx = 0;
+      if (p.ntaps == 9) {
+        dy = tap / 3 - 1;
+        dx = tap % 3 - 1;
+      }
+      uint8_t* a_dst = tiles + static_cast<size_t>(s) * STAGE_BYTES;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_4d(a_dst, &tmA, &full_bar[s], c0, x0 + dx, y0 + dy, n0);
-        tma_load_2d(b_dst, &tmB, &full_bar[s], tap * p.Cin + c0, nb0);
+        tma_load_4d(a_dst, &tmA, &full_bar[s], ch * KC, x0 + dx, y0 + dy, n0);
+        tma_load_2d(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + ch * KC, nb0);
+      }
+      __syncwarp();
+      if (++tap == p.ntaps) {
+        tap = 0;
+        ++ch;
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      bool ok = true;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % nstage;
-        const uint32_t round = static_cast<uint32_t>(it / nstage);
-        if (!mbar_wait(&full_bar[s], round & 1, abort_flag, p.watchdog_ns)) {
-          ok = false;
-          break;
-        }
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
+    // ===================== MMA issuer (warp-uniform loop, elected issue) =====================
+    bool all_ok = true;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % nstage;
+      const uint32_t round = static_cast<uint32_t>(it / nstage);
+      const bool ok = mbar_wait(&full_bar[s], round & 1, abort_flag, p.watchdog_ns);
+      if (!__all_sync(0xffffffffu, ok)) {
+        all_ok = false;
+        break;
+      }
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * STAGE_BYTES);
+      const uint64_t da0 = umma_smem_desc(a_addr, ROW_BYTES);
+      const uint64_t db0 = umma_smem_desc(a_addr + A_BYTES, ROW_BYTES);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t da = umma_smem_desc(a_addr + k * 32, ROW_BYTES);
-          const uint64_t db = umma_smem_desc(b_addr + k * 32, ROW_BYTES);
-          umma_bf16(tmem_base, da, db, IDESC, (it | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < KC / 16; ++k)  // +32 B per k step == +2 in the descriptor's 16-byte address units
+          umma_bf16(tmem_base, da0 + 2 * k, db0 + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
       }
-      if (ok) umma_commit(tmem_full_bar);
+      __syncwarp();
     }
+    if (all_ok && elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
     const int q = warp & 3;
@@ -208,72 +328,12 @@ __global__ void __launch_bounds__(kConvThreads)
     const int nn = r / (p.TW * p.TH);
     const int x = x0 + xx, y = y0 + yy, n = n0 + nn;
     const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
-    const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     const bool acc_ready = mbar_wait(tmem_full_bar, 0, abort_flag, p.watchdog_ns);
-    if (__all_sync(0xffffffffu, acc_ready)) {  // warp-uniform: the loop below uses .sync.aligned ops
+    if (__all_sync(0xffffffffu, acc_ready)) {  // warp-uniform: the epilogue uses .sync.aligned ops
       tc_fence_after();
-      float hacc[kMaxHeadClasses];
-      if constexpr (EPI == EPI_HEAD) {
-#pragma unroll
-        for (int k = 0; k < kMaxHeadClasses; ++k) hacc[k] = 0.f;
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c, raw);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[j] = __uint_as_float(raw[j]) + s_bias[c + j];
-          if (p.relu) v[j] = fmaxf(v[j], 0.f);
-        }
-        if constexpr (EPI == EPI_STORE) {
-          if (valid) store_bf16x16(p.out + pix * p.out_pitch + p.out_choff + nb0 + c, v);
-        } else if constexpr (EPI == EPI_POOL_SKIP) {
-          float m[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-            m[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, p.TW));
-          }
-          if (valid && !(xx & 1) && !(yy & 1)) {
-            const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
-            store_bf16x16(p.pool_out + ppix * p.pool_pitch + nb0 + c, m);
-          }
-          if (p.out != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], s_extra[c + j], s_extra[BN + c + j]), 0.f);
-            if (valid) store_bf16x16(p.out + pix * p.out_pitch + p.out_choff + nb0 + c, v);
-          }
-        } else if constexpr (EPI == EPI_CONVT) {
-          const int col = nb0 + c;
-          const int g = col / p.Cout;
-          const int o = col - g * p.Cout;
-          const size_t opix =
-              (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (g >> 1))) * (2 * p.W) + (2 * x + (g & 1));
-          if (valid) store_bf16x16(p.out + opix * p.out_pitch + p.out_choff + o, v);
-        } else {  // EPI_HEAD
-#pragma unroll
-          for (int k = 0; k < kMaxHeadClasses; ++k) {
-            if (k < p.ncls) {
-              float a = hacc[k];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) a = fmaf(v[j], s_extra[(c + j) * p.ncls + k], a);
-              hacc[k] = a;
-            }
-          }
-        }
-      }
-      if constexpr (EPI == EPI_HEAD) {
-        if (valid) {
-#pragma unroll
-          for (int k = 0; k < kMaxHeadClasses; ++k)
-            if (k < p.ncls) p.logits[pix * p.ncls + k] = hacc[k] + s_extra[BN * p.ncls + k];
-        }
-      }
+      epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, valid, p.TW, nb0, s_bias, s_extra);
     }
   }
 
@@ -286,11 +346,222 @@ __global__ void __launch_bounds__(kConvThreads)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent, weight-stationary variant for the high-resolution layers (small Cin*Cout, huge M).
+//
+// The tile kernel above re-fetches the A tile once per tap (9x L2->smem traffic) and spends a CTA
+// launch + TMEM allocation per 128 pixels; at Cout = 32/64 that leaves the tensor pipe idle.  Here
+//   * one CTA per SM loops over M tiles (8 wide x 16 tall pixels of one image),
+//   * all taps of the layer's weights are TMA-loaded ONCE per CTA and stay in shared memory,
+//   * per tile and channel chunk one halo SLAB ((8+2) x (16+2) pixels, zero-filled out of bounds) is
+//     loaded; the 9 taps are 9 UMMA descriptors into the same slab: start address shifted by
+//     (dy*SLAB_W + dx) pixel rows, 8-row group stride = SLAB_W pixel rows.  (Measured on B200:
+//     the UMMA swizzle XOR is a function of the absolute shared-memory address, exactly like the
+//     TMA write swizzle, so a descriptor may start at any pixel row of a TMA-written slab and use
+//     any 16-byte-multiple group stride; the descriptor's base-offset field stays 0.)
+//   * NACC TMEM accumulators and NACC epilogue warpgroups rotate over the tiles, so epilogues of
+//     up to NACC-1 earlier tiles overlap the MMAs of the current one.
+template <int NTAPS>
+struct SlabGeom {
+  static constexpr int HALO = NTAPS == 9 ? 1 : 0;
+  static constexpr int W = 8 + 2 * HALO;
+  static constexpr int H = 16 + 2 * HALO;
+};
+__host__ __device__ constexpr int slab_nacc(int BN, int EPI) { return (EPI == EPI_HEAD || BN > 64) ? 2 : 4; }
+__host__ __device__ constexpr int slab_threads(int BN, int EPI) { return 64 + 128 * slab_nacc(BN, EPI); }
+
+template <int KC, int BN, int EPI, int NTAPS>
+__global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
+    conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const ConvParams p) {
+  constexpr int ROWB = KC * 2;             // bytes per pixel row of a slab == swizzle span
+  constexpr int WT_BYTES = BN * KC * 2;    // one (chunk, tap) weight tile
+  constexpr int SW = SlabGeom<NTAPS>::W, SH = SlabGeom<NTAPS>::H, HALO = SlabGeom<NTAPS>::HALO;
+  constexpr int SLAB_BYTES = SW * SH * ROWB;
+  constexpr int SLAB_STRIDE = (SLAB_BYTES + 1023) & ~1023;
+  constexpr int NACC = slab_nacc(BN, EPI);
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int chunks = p.Cin / KC;
+  const int nwt = NTAPS * chunks;
+  const int nslab = p.nslab;
+  uint8_t* w_smem = base;
+  uint8_t* slabs = base + static_cast<size_t>(nwt) * WT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + static_cast<size_t>(nslab) * SLAB_STRIDE);
+  uint64_t* w_full = bars;
+  uint64_t* slab_full = bars + 1;
+  uint64_t* slab_empty = slab_full + nslab;
+  uint64_t* acc_full = slab_empty + nslab;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+  float* s_extra = s_bias + BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles_n;
+  const int m_first = blockIdx.x / p.n_tiles_n;
+  const int m_stride = gridDim.x / p.n_tiles_n;
+  const int nb0 = n_tile * BN;
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(w_full, 1);
+      for (int s = 0; s < nslab; ++s) {
+        mbar_init(&slab_full[s], 1);
+        mbar_init(&slab_empty[s], 1);
+      }
+      for (int a = 0; a < NACC; ++a) {
+        mbar_init(&acc_full[a], 1);
+        mbar_init(&acc_empty[a], 128);
+      }
+      *abort_flag = 0;
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, NACC * BN);
+    tmem_relinquish();
+  }
+  if (warp >= 2) load_epilogue_consts<BN, EPI>(p, threadIdx.x - 64, 128 * NACC, nb0, s_bias, s_extra);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nwt) * WT_BYTES);
+      for (int ch = 0; ch < chunks; ++ch)
+        for (int tap = 0; tap < NTAPS; ++tap)  // smem order [chunk][tap]; global K index = tap*Cin + ch*KC
+          tma_load_2d(w_smem + static_cast<size_t>(ch * NTAPS + tap) * WT_BYTES, &tmB, w_full, tap * p.Cin + ch * KC,
+                      nb0);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    bool run = true;
+    for (int m = m_first; run && m < p.num_m_tiles; m += m_stride) {
+      const int n = m / tiles_xy;
+      const int rem = m - n * tiles_xy;
+      const int ty = rem / p.tiles_x;
+      const int tx = rem - ty * p.tiles_x;
+      for (int ch = 0; ch < chunks; ++ch, ++it) {
+        const uint32_t s = it % nslab;
+        const bool ok = mbar_wait(&slab_empty[s], ((it / nslab) & 1) ^ 1, abort_flag, p.watchdog_ns);
+        if (!__all_sync(0xffffffffu, ok)) {
+          run = false;
+          break;
+        }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&slab_full[s], SLAB_BYTES);
+          tma_load_4d(slabs + static_cast<size_t>(s) * SLAB_STRIDE, &tmA, &slab_full[s], ch * KC, tx * 8 - HALO,
+                      ty * 16 - HALO, n);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    bool run = __all_sync(0xffffffffu, mbar_wait(w_full, 0, abort_flag, p.watchdog_ns));
+    uint32_t it = 0, t = 0;
+    const uint32_t w_addr = smem_u32(w_smem);
+    for (int m = m_first; run && m < p.num_m_tiles; m += m_stride, ++t) {
+      const uint32_t a = t % NACC;
+      const bool ok = mbar_wait(&acc_empty[a], ((t / NACC) & 1) ^ 1, abort_flag, p.watchdog_ns);
+      if (!__all_sync(0xffffffffu, ok)) break;
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + a * BN;
+      for (int ch = 0; ch < chunks; ++ch, ++it) {
+        const uint32_t s = it % nslab;
+        const bool ok2 = mbar_wait(&slab_full[s], (it / nslab) & 1, abort_flag, p.watchdog_ns);
+        if (!__all_sync(0xffffffffu, ok2)) {
+          run = false;
+          break;
+        }
+        tc_fence_after();
+        const uint32_t slab_addr = smem_u32(slabs + static_cast<size_t>(s) * SLAB_STRIDE);
+        const uint64_t da0 = umma_smem_desc_sbo(slab_addr, ROWB, SW * ROWB);
+        const uint64_t db0 = umma_smem_desc(w_addr + static_cast<uint32_t>(ch * NTAPS) * WT_BYTES, ROWB);
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            const int dy = NTAPS == 9 ? tap / 3 : 0;
+            const int dx = NTAPS == 9 ? tap % 3 : 0;
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              // descriptor address fields are in 16-byte units: all offsets below are compile-time
+              const uint64_t da = da0 + static_cast<uint64_t>(((dy * SW + dx) * ROWB + k * 32) >> 4);
+              const uint64_t db = db0 + static_cast<uint64_t>((tap * WT_BYTES + k * 32) >> 4);
+              umma_bf16(tacc, da, db, IDESC, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+            }
+          }
+          umma_commit(&slab_empty[s]);
+        }
+        __syncwarp();
+      }
+      if (run && elect_one()) umma_commit(&acc_full[a]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: warpgroup g handles local tiles t == g (mod NACC) =====================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int xx = r & 7, yy = r >> 3;
+    uint32_t t = g;
+    for (int m = m_first + g * m_stride; m < p.num_m_tiles; m += m_stride * NACC, t += NACC) {
+      const int n = m / tiles_xy;
+      const int rem = m - n * tiles_xy;
+      const int ty = rem / p.tiles_x;
+      const int tx = rem - ty * p.tiles_x;
+      const int x = tx * 8 + xx, y = ty * 16 + yy;
+      const bool valid = (x < p.W) && (y < p.H);
+      const bool ready = mbar_wait(&acc_full[g], (t / NACC) & 1, abort_flag, p.watchdog_ns);
+      if (!__all_sync(0xffffffffu, ready)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
+      epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, valid, 8, nb0, s_bias, s_extra);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[g]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, NACC * BN);
+    if (lane == 0 && *abort_flag) atomicExch(p.err, 1);
+  }
+}
+
+__host__ __device__ inline int slab_stride_bytes(int KC, int ntaps) {
+  const int sw = ntaps == 9 ? 10 : 8, sh = ntaps == 9 ? 18 : 16;
+  return (sw * sh * KC * 2 + 1023) & ~1023;
+}
+__host__ __device__ inline size_t slab_smem_bytes(int KC, int BN, int ntaps, int cin, int nslab, int epi, int ncls) {
+  size_t s = 1024 + static_cast<size_t>(ntaps) * (cin / KC) * BN * KC * 2 +
+             static_cast<size_t>(nslab) * slab_stride_bytes(KC, ntaps);
+  s += (2 * nslab + 2 * 4 + 1) * 8 + 16;
+  s += BN * 4;
+  if (epi == EPI_POOL_SKIP) s += 2 * BN * 4;
+  if (epi == EPI_HEAD) s += (BN * ncls + ncls) * 4;
+  return s + 64;
+}
+
 // Host side -------------------------------------------------------------------
 struct ConvLaunch {
   CUtensorMap tmA, tmB;
   ConvParams p;
   int KC, BN, EPI;
+  int slab;  // 1: conv_slab_kernel (persistent), 0: conv_umma_kernel (one tile per CTA)
   int grid;
   size_t smem;
 };

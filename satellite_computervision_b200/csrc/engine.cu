@@ -557,6 +557,50 @@ static int pick_stages(int KC, int BN, int iters, int override_stages) {
   return std::max(1, std::min(st, iters));
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Persistent weight-stationary slab kernel: used where the layer's weights (all taps) fit in shared
+// memory next to a few halo slabs and there are enough 8x16 M tiles to keep every SM busy.
+static const size_t kSlabSmemBudget = 222 * 1024;
+static const size_t kSlabWeightBudget = 150 * 1024;
+
+static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* nslab) {
+  if (!env_int("SCV_SLAB", 1)) return false;
+  if (w % 8 || h % 16) return false;
+  const int ntaps = l.kind == L_CONV3 ? 9 : 1;
+  const long long m_tiles = (long long)B * (h / 16) * (w / 8);
+  if (m_tiles < 2LL * sm_count() && !env_int("SCV_SLAB_FORCE", 0)) return false;
+  const int slab_stride = slab_stride_bytes(l.KC, ntaps);
+  const int chunks = l.cin_pad / l.KC;
+  for (int bn : {256, 128, 64, 32}) {
+    if (l.ntotal % bn) continue;
+    if (l.epi == EPI_HEAD && bn != l.ntotal) continue;
+    const size_t wbytes = (size_t)ntaps * l.cin_pad * bn * 2;
+    if (wbytes > kSlabWeightBudget) continue;
+    int ns = (int)((kSlabSmemBudget - wbytes - 8 * 1024) / slab_stride);
+    ns = std::min(ns, 8);
+    if (ns < std::max(2, chunks)) continue;
+    if (const int o = env_int("SCV_SLAB_STAGES", 0)) ns = std::max(2, std::min(ns, o));
+    *bn_out = bn;
+    *nslab = ns;
+    return true;
+  }
+  return false;
+}
+
 static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int in_pitch, int B, int h, int w,
                        ConvLaunch* L) {
   memset(L, 0, sizeof *L);
@@ -566,13 +610,6 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   p.W = w;
   p.Cin = l.cin_pad;
   p.ntaps = l.kind == L_CONV3 ? 9 : 1;
-  tile_box(w, &p.TW, &p.TH, &p.TN);
-  p.tiles_x = (w + p.TW - 1) / p.TW;
-  p.tiles_y = (h + p.TH - 1) / p.TH;
-  p.tiles_n = (B + p.TN - 1) / p.TN;
-  p.n_tiles_n = l.ntotal / l.BN;
-  const int iters = p.ntaps * (l.cin_pad / l.KC);
-  p.nstage = pick_stages(l.KC, l.BN, iters, e ? e->opt_stages : 0);
   p.relu = 1;
   p.bias = l.d_bias;
   p.Cout = l.cout;
@@ -581,10 +618,41 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   p.err = e ? e->d_err : nullptr;
   p.watchdog_ns = (unsigned long long)(e ? e->opt_watchdog_ms : 2000) * 1000000ull;
   L->KC = l.KC;
-  L->BN = l.BN;
   L->EPI = l.epi;
+  int bn = 0, ns = 0;
+  if (plan_slab(l, B, h, w, &bn, &ns)) {
+    const int sw = p.ntaps == 9 ? 10 : 8, sh = p.ntaps == 9 ? 18 : 16;
+    L->slab = 1;
+    L->BN = bn;
+    p.TW = 8, p.TH = 16, p.TN = 1;
+    p.tiles_x = w / 8;
+    p.tiles_y = h / 16;
+    p.tiles_n = B;
+    p.num_m_tiles = p.tiles_x * p.tiles_y * B;
+    p.n_tiles_n = l.ntotal / bn;
+    p.nslab = ns;
+    int grid = sm_count() / p.n_tiles_n * p.n_tiles_n;
+    const long long work = (long long)p.num_m_tiles * p.n_tiles_n;
+    if (grid > work) grid = (int)work;
+    L->grid = std::max(grid, p.n_tiles_n);
+    L->smem = slab_smem_bytes(l.KC, bn, p.ntaps, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1);
+    if (l.BN != bn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, p.ntaps * l.cin_pad, l.ntotal, l.KC, bn));
+    else L->tmB = l.tmB;
+    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, sw, sh, 1));
+    return SCV_OK;
+  }
+  L->slab = 0;
+  L->BN = l.BN;
+  tile_box(w, &p.TW, &p.TH, &p.TN);
+  p.tiles_x = (w + p.TW - 1) / p.TW;
+  p.tiles_y = (h + p.TH - 1) / p.TH;
+  p.tiles_n = (B + p.TN - 1) / p.TN;
+  p.n_tiles_n = l.ntotal / l.BN;
+  const int iters = p.ntaps * (l.cin_pad / l.KC);
+  p.nstage = pick_stages(l.KC, l.BN, iters, e ? e->opt_stages : 0);
   L->grid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
   L->tmB = l.tmB;
+  L->smem = conv_smem_bytes(l.KC, l.BN, p.nstage, l.epi, e ? e->arch.cfg.nclasses : 1);
   SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, p.TW, p.TH, p.TN));
   return SCV_OK;
 }
@@ -640,7 +708,6 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
         p.pool_pitch = a.bufs[l.pool_buf].channels;
       }
     }
-    Ln.smem = conv_smem_bytes(l.KC, l.BN, p.nstage, l.epi, a.cfg.nclasses);
     pl->launches.push_back(Ln);
   }
   *out = pl.get();
@@ -1409,7 +1476,11 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
     cleanup();
     return rc;
   }
-  if (const char* s = getenv("SCV_DEBUG_STAGES")) Ln.p.nstage = std::max(1, atoi(s));
+  if (const char* s = getenv("SCV_DEBUG_STAGES"))
+    if (!Ln.slab) {
+      Ln.p.nstage = std::max(1, atoi(s));
+      Ln.smem = conv_smem_bytes(l.KC, l.BN, Ln.p.nstage, l.epi, 1);
+    }
   Ln.p.relu = relu;
   Ln.p.out = d_y;
   Ln.p.out_pitch = Cout;
@@ -1417,7 +1488,6 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
   Ln.p.pool_out = d_p;
   Ln.p.pool_pitch = Cout;
   Ln.p.err = d_err;
-  Ln.smem = conv_smem_bytes(l.KC, l.BN, Ln.p.nstage, l.epi, 1);
   DBG_TRY(conv_launch(Ln, 0));
   DBG_TRY(cudaDeviceSynchronize());
   int herr = 0;
@@ -1428,7 +1498,7 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
 #undef DBG_TRY
   for (size_t i = 0; i < nout; ++i) y[i] = __bfloat162float(hy[i]);
   for (size_t i = 0; i < npool; ++i) pooled[i] = __bfloat162float(hp[i]);
-  if (herr) return fail(SCV_ERR_KERNEL, "device watchdog tripped in debug conv (KC=%d BN=%d stages=%d)", l.KC, l.BN, Ln.p.nstage);
+  if (herr) return fail(SCV_ERR_KERNEL, "device watchdog tripped in debug conv (KC=%d BN=%d slab=%d)", l.KC, Ln.BN, Ln.slab);
   return SCV_OK;
 }
 

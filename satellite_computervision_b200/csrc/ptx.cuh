@@ -153,15 +153,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // `row_bytes` (= swizzle span: 32, 64 or 128 B), 8-row groups `8*row_bytes` apart.
 // Field layout (cute::UMMA::SmemDescriptor): [0,14) addr>>4, [16,30) LBO>>4,
 // [32,46) SBO>>4, [46,48) version=1, [49,52) base offset, [61,64) layout type.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_bytes) {
+__device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
   const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
   d |= static_cast<uint64_t>(1) << 16;                           // LBO (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(((8 * row_bytes) >> 4) & 0x3fff) << 32;  // SBO
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;   // SBO: byte distance between 8-row groups
   d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
   d |= layout << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_bytes) {
+  return umma_smem_desc_sbo(saddr, row_bytes, 8 * row_bytes);
 }
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
