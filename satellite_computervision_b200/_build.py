@@ -38,9 +38,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(CSRC, 'build')
     os.makedirs(objdir, exist_ok=True)
 
+    extra = os.environ.get('SCV_NVCC_DEFINES', '').split()  # experiments only, e.g. -DSCV_DBG_ALIGNED_TAPS
+
     def compile_one(src):
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             print(' '.join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,14 +7,17 @@ namespace {
 template <int KC, int BN, int EPI>
 cudaError_t launch_one(const ConvLaunch& L, cudaStream_t stream) {
   if (L.slab) {
-    constexpr int NT = slab_threads(BN, EPI);
-    if constexpr (EPI == EPI_CONVT) {
-      conv_slab_kernel<KC, BN, EPI, 1><<<L.grid, NT, L.smem, stream>>>(L.tmA, L.tmB, L.p);
-    } else {
-      if (L.p.ntaps == 9)
-        conv_slab_kernel<KC, BN, EPI, 9><<<L.grid, NT, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+    constexpr int NTAPS = EPI == EPI_CONVT ? 1 : 9;
+    if (L.p.ntaps != NTAPS) return cudaErrorInvalidValue;
+    if (L.nacc == 4) {
+      if constexpr (slab_nacc_ok(BN, 4))
+        conv_slab_kernel<KC, BN, EPI, NTAPS, 4>
+            <<<L.grid, slab_threads(4), L.smem, stream>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
       else
         return cudaErrorInvalidValue;
+    } else {
+      conv_slab_kernel<KC, BN, EPI, NTAPS, 2>
+          <<<L.grid, slab_threads(2), L.smem, stream>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
     }
   } else {
     conv_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
@@ -26,10 +29,12 @@ cudaError_t attr_one() {
   const int kMax = 227 * 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
   if (e != cudaSuccess) return e;
-  if constexpr (EPI == EPI_CONVT)
-    return cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-  else
-    return cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+  constexpr int NTAPS = EPI == EPI_CONVT ? 1 : 9;
+  e = cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, NTAPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+  if (e != cudaSuccess) return e;
+  if constexpr (slab_nacc_ok(BN, 4))
+    e = cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, NTAPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+  return e;
 }
 
 template <int KC, int BN>

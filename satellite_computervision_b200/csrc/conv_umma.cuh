@@ -50,6 +50,7 @@ struct ConvParams {
   float* logits;        // N*H*W*ncls fp32
   // persistent slab kernel
   int nslab;            // slab ring depth
+  int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
   // watchdog
   int* err;
@@ -87,16 +88,16 @@ __device__ __forceinline__ void store_pk16(__nv_bfloat16* dst, const uint32_t (&
   p[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
-__device__ __forceinline__ void lds16(const float* src, float (&dst)[16]) {  // 16-byte aligned smem -> 4 x LDS.128
-  const float4* s4 = reinterpret_cast<const float4*>(src);
+// 16 floats from 16-byte-aligned shared memory as 4 x LDS.128.  Explicit ld.shared: the constant area
+// is carved out of the dynamic buffer with integer alignment arithmetic, after which the compiler no
+// longer knows the address space and would emit (slower) generic loads.
+__device__ __forceinline__ void lds16(const float* src, float (&dst)[16]) {
+  const uint32_t a = smem_u32(src);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 t = s4[j];
-    dst[4 * j + 0] = t.x;
-    dst[4 * j + 1] = t.y;
-    dst[4 * j + 2] = t.z;
-    dst[4 * j + 3] = t.w;
-  }
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(dst[4 * j + 0]), "=f"(dst[4 * j + 1]), "=f"(dst[4 * j + 2]), "=f"(dst[4 * j + 3])
+                 : "r"(a + 16 * j));
 }
 
 // Epilogue of one 128-pixel accumulator tile: this thread owns TMEM lane == pixel (x, y, n).
@@ -182,6 +183,93 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
       for (int k = 0; k < kMaxHeadClasses; ++k)
         if (k < p.ncls) p.logits[pix * p.ncls + k] = hacc[k] + s_extra[BN * p.ncls + k];
+    }
+  }
+}
+
+// Slab-kernel epilogue for the bf16 tensor outputs (EPI_STORE / EPI_POOL_SKIP / EPI_CONVT): every epilogue
+// warp owns 4 image rows x 8 pixels of the tile.  Results go, 32 channels at a time, through a per-warp
+// swizzled shared-memory staging tile (32 pixel rows of 64 B) and leave with ONE TMA store per (warp,
+// 32-channel block) -- fully coalesced global writes and no per-lane address arithmetic -- instead of
+// 16-byte stores scattered at pixel pitch.  32-channel blocks never straddle two ConvT sub-pixels.
+constexpr int kStageRowB = 64;                        // 32 bf16 channels
+constexpr int kStageOutBytes = 32 * kStageRowB;       // 4 rows x 8 pixels
+constexpr int kStagePoolBytes = 8 * kStageRowB;       // 2 rows x 4 pooled pixels
+__host__ __device__ constexpr int slab_stage_warp_bytes(int epi) {
+  return epi == EPI_HEAD ? 0 : (kStageOutBytes + (epi == EPI_POOL_SKIP ? kStagePoolBytes : 0));
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_slab(const ConvParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmPool,
+                                              uint32_t taddr, int lane, int q, int x0, int y0, int n, int nb0,
+                                              const float* s_bias, const float* s_extra, uint8_t* stage) {
+  const int xx = lane & 7, yl = lane >> 3;
+  // swizzle phase of a 64-byte staging row = absolute smem address bits [7,9) (SWIZZLE_64B)
+  const uint32_t phase = (lane >> 1) & 3;
+  const int prow = (yl >> 1) * 4 + (xx >> 1);  // pooled pixel row in the pool staging tile
+  const uint32_t pphase = (prow >> 1) & 3;
+  const bool pool_leader = !(xx & 1) && !(yl & 1);
+  const uint32_t out_row = smem_u32(stage) + lane * kStageRowB;
+  const uint32_t pool_row = smem_u32(stage) + kStageOutBytes + prow * kStageRowB;
+#pragma unroll 1
+  for (int blk = 0; blk < BN / 32; ++blk) {
+    uint32_t pk[16], pm[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = blk * 32 + h * 16;
+      uint32_t raw[16];
+      tmem_ld16(taddr + col, raw);
+      tmem_ld_wait();
+      float v[16], cst[16];
+      lds16(s_bias + col, cst);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = __uint_as_float(raw[j]) + cst[j];
+        if (p.relu) v[j] = fmaxf(v[j], 0.f);
+      }
+      if constexpr (EPI == EPI_POOL_SKIP) {
+        // 2x2 max-pool on the bf16-rounded values (rounding is monotonic, so max commutes with it)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t w = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          const uint32_t t = max_bf16x2(w, __shfl_xor_sync(0xffffffffu, w, 1));
+          pm[8 * h + j] = max_bf16x2(t, __shfl_xor_sync(0xffffffffu, t, 8));
+        }
+        float sh[16];
+        lds16(s_extra + col, cst);
+        lds16(s_extra + BN + col, sh);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], cst[j], sh[j]), 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[8 * h + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    }
+    if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(out_row + ((static_cast<uint32_t>(j) ^ phase) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    if constexpr (EPI == EPI_POOL_SKIP) {
+      if (pool_leader) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(pool_row + ((static_cast<uint32_t>(j) ^ pphase) << 4), pm[4 * j], pm[4 * j + 1], pm[4 * j + 2],
+                 pm[4 * j + 3]);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const int ch0 = nb0 + blk * 32;
+      if constexpr (EPI == EPI_CONVT) {
+        const int g = ch0 / p.Cout;  // sub-pixel (a, b) = (g >> 1, g & 1); rows of (n, y) are merged in the map
+        tma_store_5d(tmOut, stage, p.out_choff + (ch0 - g * p.Cout), g & 1, x0, g >> 1, n * p.H + y0 + q * 4);
+      } else {
+        tma_store_4d(tmOut, stage, p.out_choff + ch0, x0, y0 + q * 4, n);
+        if constexpr (EPI == EPI_POOL_SKIP)
+          tma_store_4d(tmPool, stage + kStageOutBytes, ch0, x0 >> 1, (y0 >> 1) + q * 2, n);
+      }
+      bulk_commit();
     }
   }
 }
@@ -367,19 +455,27 @@ struct SlabGeom {
   static constexpr int W = 8 + 2 * HALO;
   static constexpr int H = 16 + 2 * HALO;
 };
-__host__ __device__ constexpr int slab_nacc(int BN, int EPI) { return (EPI == EPI_HEAD || BN > 64) ? 2 : 4; }
-__host__ __device__ constexpr int slab_threads(int BN, int EPI) { return 64 + 128 * slab_nacc(BN, EPI); }
+// NACC = number of TMEM accumulators == number of epilogue warpgroups (2 or 4; NACC*BN <= 512 columns).
+__host__ __device__ constexpr bool slab_nacc_ok(int BN, int nacc) { return nacc * BN <= 512; }
+// warp 0: TMA producer; warps 1..kSlabIssuers: MMA issuers (tiles alternate between them: the UMMA queue
+// is only a few instructions deep, so a single issuer's per-tile barrier work would leave the tensor pipe
+// idle between tiles); then 4 epilogue warps per accumulator.
+// mbarrier parity waits are only meaningful one phase ahead, so every barrier must always be waited on by
+// the SAME issuer in consecutive rounds: accumulators alternate (NACC even), and a slab slot returns to the
+// same issuer only if nslab is a multiple of kSlabIssuers * chunks -- otherwise the host selects one issuer.
+constexpr int kSlabIssuers = 2;
+__host__ __device__ constexpr int slab_threads(int nacc) { return 32 * (1 + kSlabIssuers) + 128 * nacc; }
 
-template <int KC, int BN, int EPI, int NTAPS>
-__global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
+template <int KC, int BN, int EPI, int NTAPS, int NACC>
+__global__ void __launch_bounds__(slab_threads(NACC), 1)
     conv_slab_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPool,
                      const ConvParams p) {
   constexpr int ROWB = KC * 2;             // bytes per pixel row of a slab == swizzle span
   constexpr int WT_BYTES = BN * KC * 2;    // one (chunk, tap) weight tile
   constexpr int SW = SlabGeom<NTAPS>::W, SH = SlabGeom<NTAPS>::H, HALO = SlabGeom<NTAPS>::HALO;
   constexpr int SLAB_BYTES = SW * SH * ROWB;
   constexpr int SLAB_STRIDE = (SLAB_BYTES + 1023) & ~1023;
-  constexpr int NACC = slab_nacc(BN, EPI);
   constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -389,7 +485,9 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
   const int nslab = p.nslab;
   uint8_t* w_smem = base;
   uint8_t* slabs = base + static_cast<size_t>(nwt) * WT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + static_cast<size_t>(nslab) * SLAB_STRIDE);
+  uint8_t* staging = slabs + static_cast<size_t>(nslab) * SLAB_STRIDE;  // 1024-aligned
+  constexpr int STAGE_TOTAL = 4 * NACC * slab_stage_warp_bytes(EPI);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGE_TOTAL);
   uint64_t* w_full = bars;
   uint64_t* slab_full = bars + 1;
   uint64_t* slab_empty = slab_full + nslab;
@@ -411,6 +509,8 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI != EPI_HEAD) tma_prefetch_desc(&tmOut);
+    if constexpr (EPI == EPI_POOL_SKIP) tma_prefetch_desc(&tmPool);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -430,7 +530,9 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
     tmem_alloc(tmem_slot, NACC * BN);
     tmem_relinquish();
   }
-  if (warp >= 2) load_epilogue_consts<BN, EPI>(p, threadIdx.x - 64, 128 * NACC, nb0, s_bias, s_extra);
+  constexpr int kFirstEpiWarp = 1 + kSlabIssuers;
+  if (warp >= kFirstEpiWarp)
+    load_epilogue_consts<BN, EPI>(p, threadIdx.x - 32 * kFirstEpiWarp, 128 * NACC, nb0, s_bias, s_extra);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -468,12 +570,15 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    bool run = __all_sync(0xffffffffu, mbar_wait(w_full, 0, abort_flag, p.watchdog_ns));
-    uint32_t it = 0, t = 0;
+  } else if (warp < kFirstEpiWarp) {
+    // ===================== MMA issuers: issuer j takes local tiles t == j (mod kSlabIssuers) =====================
+    const int nissue = p.n_issuers;
+    bool run = (warp - 1) < nissue && __all_sync(0xffffffffu, mbar_wait(w_full, 0, abort_flag, p.watchdog_ns));
+    uint32_t t = warp - 1;
     const uint32_t w_addr = smem_u32(w_smem);
-    for (int m = m_first; run && m < p.num_m_tiles; m += m_stride, ++t) {
+    for (int m = m_first + static_cast<int>(t) * m_stride; run && m < p.num_m_tiles;
+         m += m_stride * nissue, t += nissue) {
+      uint32_t it = t * chunks;  // position of this tile's first slab in the producer's sequence
       const uint32_t a = t % NACC;
       const bool ok = mbar_wait(&acc_empty[a], ((t / NACC) & 1) ^ 1, abort_flag, p.watchdog_ns);
       if (!__all_sync(0xffffffffu, ok)) break;
@@ -492,7 +597,11 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
         const uint64_t db0 = umma_smem_desc(w_addr + static_cast<uint32_t>(ch * NTAPS) * WT_BYTES, ROWB);
         if (elect_one()) {
 #pragma unroll
+#if defined(SCV_DBG_ONE_MMA)  // timing experiment hook (results are wrong when defined)
+          for (int tap = 0; tap < 1; ++tap) {
+#else
           for (int tap = 0; tap < NTAPS; ++tap) {
+#endif
             const int dy = NTAPS == 9 ? tap / 3 : 0;
             const int dx = NTAPS == 9 ? tap % 3 : 0;
 #pragma unroll
@@ -512,7 +621,7 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
     }
   } else {
     // ===================== epilogue: warpgroup g handles local tiles t == g (mod NACC) =====================
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - kFirstEpiWarp) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int xx = r & 7, yy = r >> 3;
@@ -522,15 +631,24 @@ __global__ void __launch_bounds__(slab_threads(BN, EPI), 1)
       const int rem = m - n * tiles_xy;
       const int ty = rem / p.tiles_x;
       const int tx = rem - ty * p.tiles_x;
-      const int x = tx * 8 + xx, y = ty * 16 + yy;
-      const bool valid = (x < p.W) && (y < p.H);
       const bool ready = mbar_wait(&acc_full[g], (t / NACC) & 1, abort_flag, p.watchdog_ns);
       if (!__all_sync(0xffffffffu, ready)) break;
       tc_fence_after();
       const uint32_t taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
-      epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, valid, 8, nb0, s_bias, s_extra);
+#if !defined(SCV_DBG_NO_EPILOGUE)  // timing experiment hook (results are wrong when defined)
+      if constexpr (EPI == EPI_HEAD) {
+        const int x = tx * 8 + xx, y = ty * 16 + yy;
+        epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, (x < p.W) && (y < p.H), 8, nb0, s_bias, s_extra);
+      } else {
+        epilogue_slab<BN, EPI>(p, &tmOut, &tmPool, taddr, lane, q, tx * 8, ty * 16, n, nb0, s_bias, s_extra,
+                               staging + static_cast<size_t>(warp - kFirstEpiWarp) * slab_stage_warp_bytes(EPI));
+      }
+#endif
       tc_fence_before();
       mbar_arrive(&acc_empty[g]);
+    }
+    if constexpr (EPI != EPI_HEAD) {
+      if (lane == 0) bulk_wait_read<0>();  // staging must stay valid until the last stores have read it
     }
   }
 
@@ -546,9 +664,13 @@ __host__ __device__ inline int slab_stride_bytes(int KC, int ntaps) {
   const int sw = ntaps == 9 ? 10 : 8, sh = ntaps == 9 ? 18 : 16;
   return (sw * sh * KC * 2 + 1023) & ~1023;
 }
-__host__ __device__ inline size_t slab_smem_bytes(int KC, int BN, int ntaps, int cin, int nslab, int epi, int ncls) {
+__host__ __device__ inline size_t slab_stage_bytes(int epi, int nacc) {
+  return static_cast<size_t>(4 * nacc) * slab_stage_warp_bytes(epi);
+}
+__host__ __device__ inline size_t slab_smem_bytes(int KC, int BN, int ntaps, int cin, int nslab, int epi, int ncls,
+                                                  int nacc) {
   size_t s = 1024 + static_cast<size_t>(ntaps) * (cin / KC) * BN * KC * 2 +
-             static_cast<size_t>(nslab) * slab_stride_bytes(KC, ntaps);
+             static_cast<size_t>(nslab) * slab_stride_bytes(KC, ntaps) + slab_stage_bytes(epi, nacc);
   s += (2 * nslab + 2 * 4 + 1) * 8 + 16;
   s += BN * 4;
   if (epi == EPI_POOL_SKIP) s += 2 * BN * 4;
@@ -559,9 +681,11 @@ __host__ __device__ inline size_t slab_smem_bytes(int KC, int BN, int ntaps, int
 // Host side -------------------------------------------------------------------
 struct ConvLaunch {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmOut, tmPool;  // slab kernel only: TMA-store maps of the bf16 outputs
   ConvParams p;
   int KC, BN, EPI;
   int slab;  // 1: conv_slab_kernel (persistent), 0: conv_umma_kernel (one tile per CTA)
+  int nacc;  // slab kernel: accumulators / epilogue warpgroups (2 or 4)
   int grid;
   size_t smem;
 };

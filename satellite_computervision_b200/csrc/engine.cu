@@ -98,6 +98,36 @@ static int make_w_tmap(CUtensorMap* tm, const void* ptr, int Ktotal, int Ntotal,
   return SCV_OK;
 }
 
+// bf16 NHWC output tensor maps for the slab kernel's per-warp TMA stores (box = CB channels x 8 px x 4 rows).
+static int make_store_tmap(CUtensorMap* tm, const void* ptr, int N, int H, int W, int Cpitch, int CB, int bw, int bh) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)Cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Cpitch * 2, (cuuint64_t)W * Cpitch * 2, (cuuint64_t)H * W * Cpitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled(store map) -> %d", (int)r);
+  return SCV_OK;
+}
+// Conv2DTranspose output (N, 2H, 2W, Cpitch) viewed as 5-D (C, b, x, a, n*H + y): pixel (2y+a, 2x+b).
+static int make_convt_store_tmap(CUtensorMap* tm, const void* ptr, int N, int H, int W, int Cpitch, int CB) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t px = (cuuint64_t)Cpitch * 2;
+  cuuint64_t dims[5] = {(cuuint64_t)Cpitch, 2, (cuuint64_t)W, 2, (cuuint64_t)N * H};
+  cuuint64_t strides[4] = {px, 2 * px, 2 * (cuuint64_t)W * px, 4 * (cuuint64_t)W * px};
+  cuuint32_t box[5] = {(cuuint32_t)CB, 1, 8, 1, 4};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCV_ERR_CUDA, "cuTensorMapEncodeTiled(convT store map) -> %d", (int)r);
+  return SCV_OK;
+}
+
 // ============================================================== architecture
 static int pad_channels(int c) {
   if (c <= 16) return 16;
@@ -577,26 +607,43 @@ static int sm_count() {
 static const size_t kSlabSmemBudget = 222 * 1024;
 static const size_t kSlabWeightBudget = 150 * 1024;
 
-static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* nslab) {
+// Measured on B200 (tools/microbench/umma_rate.cu): an SS-operand 128 x N x 16 bf16 UMMA sustains one
+// issue per ~{46, 54, 70, 134} cycles for N = {32, 64, 128, 256} (operand fetch ~115 B/clk from smem).
+static int umma_cycles(int bn) { return bn <= 32 ? 46 : (bn <= 64 ? 54 : (bn <= 128 ? 70 : 134)); }
+
+static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* nslab, int* nacc_out) {
   if (!env_int("SCV_SLAB", 1)) return false;
   if (w % 8 || h % 16) return false;
   const int ntaps = l.kind == L_CONV3 ? 9 : 1;
   const long long m_tiles = (long long)B * (h / 16) * (w / 8);
-  if (m_tiles < 2LL * sm_count() && !env_int("SCV_SLAB_FORCE", 0)) return false;
+  const bool force = env_int("SCV_SLAB_FORCE", 0) != 0;
   const int slab_stride = slab_stride_bytes(l.KC, ntaps);
   const int chunks = l.cin_pad / l.KC;
   for (int bn : {256, 128, 64, 32}) {
     if (l.ntotal % bn) continue;
     if (l.epi == EPI_HEAD && bn != l.ntotal) continue;
+    const int n_tiles_n = l.ntotal / bn;
+    // persistent CTAs need enough tiles each, and re-reading A once per N tile must stay cheap
+    if (!force && (n_tiles_n > 2 || m_tiles * n_tiles_n < 8LL * sm_count())) continue;
     const size_t wbytes = (size_t)ntaps * l.cin_pad * bn * 2;
     if (wbytes > kSlabWeightBudget) continue;
-    int ns = (int)((kSlabSmemBudget - wbytes - 8 * 1024) / slab_stride);
-    ns = std::min(ns, 8);
-    if (ns < std::max(2, chunks)) continue;
-    if (const int o = env_int("SCV_SLAB_STAGES", 0)) ns = std::max(2, std::min(ns, o));
-    *bn_out = bn;
-    *nslab = ns;
-    return true;
+    // epilogue budget: with few MMAs per tile the epilogue warps must turn tiles around fast -> 4 groups
+    const long long mma_cycles = (long long)ntaps * (l.cin_pad / 16) * umma_cycles(bn);
+    const int first = (mma_cycles < 3000 && slab_nacc_ok(bn, 4)) ? 4 : 2;
+    for (int nacc : {first, first == 4 ? 2 : 4}) {
+      if (!slab_nacc_ok(bn, nacc)) continue;
+      const size_t fixed = wbytes + slab_stage_bytes(l.epi, nacc) + 6 * 1024;
+      const int need = std::max(2, chunks);  // at least one whole tile's worth of slabs
+      if (fixed + (size_t)need * slab_stride > kSlabSmemBudget) continue;
+      int ns = std::min(8, (int)((kSlabSmemBudget - fixed) / slab_stride));
+      if (const int o = env_int("SCV_SLAB_STAGES", 0)) ns = std::max(need, std::min(ns, o));
+      // two issuer warps need every slab slot to come back to the same issuer (see conv_slab_kernel)
+      if (ns >= 2 * chunks) ns = ns / (2 * chunks) * (2 * chunks);
+      *bn_out = bn;
+      *nslab = ns;
+      *nacc_out = nacc;
+      return true;
+    }
   }
   return false;
 }
@@ -619,8 +666,9 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   p.watchdog_ns = (unsigned long long)(e ? e->opt_watchdog_ms : 2000) * 1000000ull;
   L->KC = l.KC;
   L->EPI = l.epi;
-  int bn = 0, ns = 0;
-  if (plan_slab(l, B, h, w, &bn, &ns)) {
+  int bn = 0, ns = 0, nacc = 2;
+  if (plan_slab(l, B, h, w, &bn, &ns, &nacc)) {
+    L->nacc = nacc;
     const int sw = p.ntaps == 9 ? 10 : 8, sh = p.ntaps == 9 ? 18 : 16;
     L->slab = 1;
     L->BN = bn;
@@ -631,11 +679,12 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     p.num_m_tiles = p.tiles_x * p.tiles_y * B;
     p.n_tiles_n = l.ntotal / bn;
     p.nslab = ns;
+    p.n_issuers = (ns % (2 * (l.cin_pad / l.KC)) == 0) ? 2 : 1;
     int grid = sm_count() / p.n_tiles_n * p.n_tiles_n;
     const long long work = (long long)p.num_m_tiles * p.n_tiles_n;
     if (grid > work) grid = (int)work;
     L->grid = std::max(grid, p.n_tiles_n);
-    L->smem = slab_smem_bytes(l.KC, bn, p.ntaps, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1);
+    L->smem = slab_smem_bytes(l.KC, bn, p.ntaps, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1, nacc);
     if (l.BN != bn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, p.ntaps * l.cin_pad, l.ntotal, l.KC, bn));
     else L->tmB = l.tmB;
     SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, sw, sh, 1));
@@ -654,6 +703,18 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   L->tmB = l.tmB;
   L->smem = conv_smem_bytes(l.KC, l.BN, p.nstage, l.epi, e ? e->arch.cfg.nclasses : 1);
   SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, p.TW, p.TH, p.TN));
+  return SCV_OK;
+}
+
+// TMA-store maps of a slab launch's bf16 outputs (call once the output pointers are known).
+static int finish_slab_maps(ConvLaunch* L, const LayerDef& l) {
+  if (!L->slab || l.epi == EPI_HEAD) return SCV_OK;
+  const ConvParams& p = L->p;
+  const int cb = 32;  // kStageRowB / 2 channels per store box
+  if (l.epi == EPI_CONVT) return make_convt_store_tmap(&L->tmOut, p.out, p.N, p.H, p.W, p.out_pitch, cb);
+  SCV_TRY(make_store_tmap(&L->tmOut, p.out, p.N, p.H, p.W, p.out_pitch, cb, 8, 4));
+  if (l.epi == EPI_POOL_SKIP)
+    SCV_TRY(make_store_tmap(&L->tmPool, p.pool_out, p.N, p.H / 2, p.W / 2, p.pool_pitch, cb, 4, 2));
   return SCV_OK;
 }
 
@@ -708,6 +769,11 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
         p.pool_pitch = a.bufs[l.pool_buf].channels;
       }
     }
+    SCV_TRY(finish_slab_maps(&Ln, l));
+    if (env_int("SCV_PLAN_DEBUG", 0))
+      fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,
+              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab ? "slab" : "tile", Ln.KC, Ln.BN,
+              Ln.slab ? "nslab" : "nstage", Ln.slab ? Ln.p.nslab : Ln.p.nstage, Ln.slab ? Ln.nacc : 1, Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
   *out = pl.get();
@@ -1488,6 +1554,11 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
   Ln.p.pool_out = d_p;
   Ln.p.pool_pitch = Cout;
   Ln.p.err = d_err;
+  rc = finish_slab_maps(&Ln, l);
+  if (rc != SCV_OK) {
+    cleanup();
+    return rc;
+  }
   DBG_TRY(conv_launch(Ln, 0));
   DBG_TRY(cudaDeviceSynchronize());
   int herr = 0;
