@@ -100,6 +100,15 @@ __device__ __forceinline__ void lds16(const float* src, float (&dst)[16]) {
                  : "r"(a + 16 * j));
 }
 
+__device__ __forceinline__ void lds32(const float* src, float (&dst)[32]) {
+  const uint32_t a = smem_u32(src);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(dst[4 * j + 0]), "=f"(dst[4 * j + 1]), "=f"(dst[4 * j + 2]), "=f"(dst[4 * j + 3])
+                 : "r"(a + 16 * j));
+}
+
 // Epilogue of one 128-pixel accumulator tile: this thread owns TMEM lane == pixel (x, y, n).
 // `pair_w` is the lane distance of the vertical 2x2-pool partner (the M-tile's width in pixels).
 template <int BN, int EPI>
@@ -213,37 +222,38 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const CUtenso
   const uint32_t pool_row = smem_u32(stage) + kStageOutBytes + prow * kStageRowB;
 #pragma unroll 1
   for (int blk = 0; blk < BN / 32; ++blk) {
+    // all loads of the block are issued before the first use (TMEM + shared-memory latency overlap)
     uint32_t pk[16], pm[16];
+    const int col = blk * 32;
+    uint32_t raw[32];
+    tmem_ld32(taddr + col, raw);
+    float v[32];
+    lds32(s_bias + col, v);
+    tmem_ld_wait();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col = blk * 32 + h * 16;
-      uint32_t raw[16];
-      tmem_ld16(taddr + col, raw);
-      tmem_ld_wait();
-      float v[16], cst[16];
-      lds16(s_bias + col, cst);
+    for (int j = 0; j < 32; ++j) {
+      v[j] += __uint_as_float(raw[j]);
+      if (p.relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if constexpr (EPI == EPI_POOL_SKIP) {
+      // 2x2 max-pool on the bf16-rounded values (rounding is monotonic, so max commutes with it)
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        v[j] = __uint_as_float(raw[j]) + cst[j];
-        if (p.relu) v[j] = fmaxf(v[j], 0.f);
-      }
-      if constexpr (EPI == EPI_POOL_SKIP) {
-        // 2x2 max-pool on the bf16-rounded values (rounding is monotonic, so max commutes with it)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t w = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          const uint32_t t = max_bf16x2(w, __shfl_xor_sync(0xffffffffu, w, 1));
-          pm[8 * h + j] = max_bf16x2(t, __shfl_xor_sync(0xffffffffu, t, 8));
-        }
-        float sh[16];
-        lds16(s_extra + col, cst);
-        lds16(s_extra + BN + col, sh);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], cst[j], sh[j]), 0.f);
+        const uint32_t w = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        const uint32_t t = max_bf16x2(w, __shfl_xor_sync(0xffffffffu, w, 1));
+        pm[j] = max_bf16x2(t, __shfl_xor_sync(0xffffffffu, t, 8));
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pk[8 * h + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      for (int h = 0; h < 2; ++h) {
+        float sc[16], sh[16];
+        lds16(s_extra + col + 16 * h, sc);
+        lds16(s_extra + BN + col + 16 * h, sh);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * h + j] = fmaxf(fmaf(v[16 * h + j], sc[j], sh[j]), 0.f);
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
     if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
     __syncwarp();
 #pragma unroll
@@ -272,6 +282,39 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const CUtenso
       bulk_commit();
     }
   }
+}
+
+// Epilogue of the last decoder conv with the 1x1 head fused (EPI_HEAD), used by both kernels (same summation
+// order, so logits do not depend on the kernel): 32 accumulator columns per
+// step, all loads issued before first use; the common single-class (sigmoid) head is one fp32 dot product per
+// pixel, other class counts take the generic path.
+template <int BN>
+__device__ __forceinline__ void epilogue_head(const ConvParams& p, uint32_t taddr, int xx, int yy, int x, int y,
+                                                   int n, bool valid, int nb0, const float* s_bias,
+                                                   const float* s_extra) {
+  if (p.ncls != 1) {
+    epilogue_tile<BN, EPI_HEAD>(p, taddr, xx, yy, x, y, n, valid, 8, nb0, s_bias, s_extra);
+    return;
+  }
+  float acc = s_extra[BN];  // head bias
+#pragma unroll 1
+  for (int col = 0; col < BN; col += 32) {
+    uint32_t raw[32];
+    tmem_ld32(taddr + col, raw);
+    float v[32], w[32];
+    lds32(s_bias + col, v);
+    lds32(s_extra + col, w);
+    tmem_ld_wait();
+    float part[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent FMA chains
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = v[j] + __uint_as_float(raw[j]);
+      if (p.relu) t = fmaxf(t, 0.f);
+      part[j & 3] = fmaf(t, w[j], part[j & 3]);
+    }
+    acc += (part[0] + part[1]) + (part[2] + part[3]);
+  }
+  if (valid) p.logits[(static_cast<size_t>(n) * p.H + y) * p.W + x] = acc;
 }
 
 template <int BN, int EPI>
@@ -421,7 +464,10 @@ __global__ void __launch_bounds__(kConvThreads)
     const bool acc_ready = mbar_wait(tmem_full_bar, 0, abort_flag, p.watchdog_ns);
     if (__all_sync(0xffffffffu, acc_ready)) {  // warp-uniform: the epilogue uses .sync.aligned ops
       tc_fence_after();
-      epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, valid, p.TW, nb0, s_bias, s_extra);
+      if constexpr (EPI == EPI_HEAD)
+        epilogue_head<BN>(p, taddr, xx, yy, x, y, n, valid, nb0, s_bias, s_extra);
+      else
+        epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, valid, p.TW, nb0, s_bias, s_extra);
     }
   }
 
@@ -638,7 +684,7 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
 #if !defined(SCV_DBG_NO_EPILOGUE)  // timing experiment hook (results are wrong when defined)
       if constexpr (EPI == EPI_HEAD) {
         const int x = tx * 8 + xx, y = ty * 16 + yy;
-        epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, (x < p.W) && (y < p.H), 8, nb0, s_bias, s_extra);
+        epilogue_head<BN>(p, taddr, xx, yy, x, y, n, (x < p.W) && (y < p.H), nb0, s_bias, s_extra);
       } else {
         epilogue_slab<BN, EPI>(p, &tmOut, &tmPool, taddr, lane, q, tx * 8, ty * 16, n, nb0, s_bias, s_extra,
                                staging + static_cast<size_t>(warp - kFirstEpiWarp) * slab_stage_warp_bytes(EPI));

@@ -31,27 +31,55 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 __device__ __forceinline__ int smem_row_stride(int row_bytes) { return (row_bytes + 16 + 15) & ~15; }
 
-// K1.  One block = `rows_per_block` rows of one chip.  Stage: the rows' bytes are
-// fetched with 128-bit loads from the 16-byte-aligned span covering them (any
-// element alignment of the chip origin is handled) into shared memory.  Compute:
-// one thread per pixel reads its C bands from shared memory, normalises in fp32
-// exactly as the reference writes it (subtract, then IEEE divide), and writes
-// cpad bf16 channels with 128-bit stores (a warp writes 32*cpad*2 contiguous bytes).
+// Element -> fp32 without the (quarter-rate) I2F unit for the integer types: for 0 <= x < 2^23,
+// float(x) == as_float(0x4B000000 | x) - 2^23 exactly.
+template <int DT>
+__device__ __forceinline__ float load_elem_t(const uint8_t* p) {
+  if constexpr (DT == SCV_U8) return __uint_as_float(0x4B000000u | *p) - 8388608.0f;
+  else if constexpr (DT == SCV_U16)
+    return __uint_as_float(0x4B000000u | *reinterpret_cast<const uint16_t*>(p)) - 8388608.0f;
+  else if constexpr (DT == SCV_I16)  // bias by 2^15 to make it unsigned, undo after the conversion
+    return __uint_as_float(0x4B000000u | (*reinterpret_cast<const uint16_t*>(p) ^ 0x8000u)) - 8421376.0f;
+  else if constexpr (DT == SCV_F32) return *reinterpret_cast<const float*>(p);
+  else return static_cast<float>(*reinterpret_cast<const double*>(p));
+}
+
+// bf16(RN_f32((x - sub) / div)) without paying an IEEE division per element: q' = (x - sub) * RN(1/div) is
+// within 2.5 fp32 ulps of the correctly rounded quotient, so both round to the same bf16 unless q' lies within
+// a few ulps of a bf16 rounding boundary (low 16 bits near 0x8000) -- only then (about 1 value in 7000) is the
+// exact division evaluated.  Results are bit-identical to dividing always.
+__device__ __forceinline__ float exact_div_for_bf16(float t, float div, float rdiv) {
+  const float q = __fmul_rn(t, rdiv);
+  const uint32_t bits = __float_as_uint(q);
+  const uint32_t expo = (bits >> 23) & 0xffu;
+  if (((bits & 0xffffu) - 0x7ffcu) <= 8u || expo - 2u >= 252u) return __fdiv_rn(t, div);  // near boundary, tiny, inf/nan
+  return q;
+}
+
+// K1.  One block = `rows_per_block` rows of one chip.  Stage: the rows' bytes are fetched with 128-bit
+// loads from the 16-byte-aligned span covering them (any element alignment of the chip origin is handled)
+// into shared memory.  Compute: one thread per pixel reads its C bands from shared memory, normalises in
+// fp32 exactly as the reference writes it (subtract, then IEEE divide), and writes cpad bf16 channels with
+// 128-bit stores (a warp writes 32*cpad*2 contiguous bytes).  CT > 0 fixes the band count at compile time.
+template <int DT, int CT>
 __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
   extern __shared__ __align__(16) uint8_t sm[];
+  constexpr int esize = DT == SCV_U8 ? 1 : (DT == SCV_U16 || DT == SCV_I16) ? 2 : (DT == SCV_F32 ? 4 : 8);
+  constexpr int NV = CT > 0 ? ((CT + 7) / 8) * 8 : SCV_MAX_BANDS;  // values held per pixel
+  const int C = CT > 0 ? CT : p.C;
   const int tile = blockIdx.y;
   const int r0 = blockIdx.x * p.rows_per_block;
   const int2 org = p.origins[tile];
-  const int esize = dtype_size(p.dtype);
-  const int row_bytes = p.side * p.C * esize;
+  const int row_bytes = p.side * C * esize;
   const int sstride = smem_row_stride(row_bytes);
   const int nrows = min(p.rows_per_block, p.side - r0);
   const uint8_t* src_end = p.src + p.src_bytes;
+  const long long pitch = static_cast<long long>(p.W) * C * esize;
+  const uint8_t* g_first = p.src + static_cast<long long>(org.y + r0 - p.src_row0) * pitch +
+                           static_cast<long long>(org.x) * C * esize;
 
   for (int rr = 0; rr < nrows; ++rr) {
-    const long long gofs =
-        (static_cast<long long>(org.y + r0 + rr - p.src_row0) * p.W + org.x) * p.C * esize;
-    const uint8_t* g = p.src + gofs;
+    const uint8_t* g = g_first + rr * pitch;
     const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
     const uint8_t* g0 = g - mis;
     const int nvec = (mis + row_bytes + 15) >> 4;
@@ -72,73 +100,74 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
   }
   __syncthreads();
 
-  const int C = p.C;
   const int nchunk = p.cpad >> 3;
-  for (int i = threadIdx.x; i < nrows * p.side; i += blockDim.x) {
-    const int rr = i / p.side;
-    const int x = i - rr * p.side;
-    const long long gofs =
-        (static_cast<long long>(org.y + r0 + rr - p.src_row0) * p.W + org.x) * p.C * esize;
-    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(p.src + gofs) & 15);
-    const uint8_t* s = sm + rr * sstride + mis + x * C * esize;
-    float v[SCV_MAX_BANDS];
+  const int mode = p.norm_mode;
+  const float* st = (mode == SCV_NORM_TILE_ZSCORE || mode == SCV_NORM_TILE_MINMAX)
+                        ? p.tile_stats + static_cast<size_t>(tile) * C * 2
+                        : nullptr;
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(g_first + rr * pitch) & 15);
+    const uint8_t* srow = sm + rr * sstride + mis;
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(tile) * p.side + (r0 + rr)) * p.side * p.cpad;
+    for (int x = threadIdx.x; x < p.side; x += blockDim.x) {
+      const uint8_t* s = srow + x * C * esize;
+      float v[NV];
 #pragma unroll
-    for (int c = 0; c < SCV_MAX_BANDS; ++c) v[c] = (c < C) ? load_elem(s + c * esize, p.dtype) : 0.f;
+      for (int c = 0; c < NV; ++c) v[c] = (c < C) ? load_elem_t<DT>(s + c * esize) : 0.f;
 
-    if (p.norm_mode == SCV_NORM_PER_BAND) {
+      if (mode == SCV_NORM_PER_BAND) {
 #pragma unroll
-      for (int c = 0; c < SCV_MAX_BANDS; ++c)
-        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], p.sub[c]), p.div[c]);
-    } else if (p.norm_mode == SCV_NORM_TILE_ZSCORE || p.norm_mode == SCV_NORM_TILE_MINMAX) {
-      const float* st = p.tile_stats + static_cast<size_t>(tile) * C * 2;
+        for (int c = 0; c < NV; ++c)
+          if (c < C) v[c] = exact_div_for_bf16(__fsub_rn(v[c], p.sub[c]), p.div[c], p.rdiv[c]);
+      } else if (st != nullptr) {
 #pragma unroll
-      for (int c = 0; c < SCV_MAX_BANDS; ++c)
-        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], st[2 * c]), st[2 * c + 1]);
-    } else if (p.norm_mode == SCV_NORM_PIXEL_MINMAX) {
-      float mn = v[0], mx = v[0];
+        for (int c = 0; c < NV; ++c)
+          if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], st[2 * c]), st[2 * c + 1]);
+      } else if (mode == SCV_NORM_PIXEL_MINMAX) {
+        float mn = v[0], mx = v[0];
 #pragma unroll
-      for (int c = 1; c < SCV_MAX_BANDS; ++c)
-        if (c < C) {
-          mn = fminf(mn, v[c]);
-          mx = fmaxf(mx, v[c]);
-        }
-      const float den = __fadd_rn(__fsub_rn(mx, mn), p.div[0]);
+        for (int c = 1; c < NV; ++c)
+          if (c < C) {
+            mn = fminf(mn, v[c]);
+            mx = fmaxf(mx, v[c]);
+          }
+        const float den = __fadd_rn(__fsub_rn(mx, mn), p.div[0]);
 #pragma unroll
-      for (int c = 0; c < SCV_MAX_BANDS; ++c)
-        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mn), den);
-    } else if (p.norm_mode == SCV_NORM_PIXEL_ZSCORE) {
-      float sum = 0.f;
+        for (int c = 0; c < NV; ++c)
+          if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mn), den);
+      } else if (mode == SCV_NORM_PIXEL_ZSCORE) {
+        float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < SCV_MAX_BANDS; ++c)
-        if (c < C) sum = __fadd_rn(sum, v[c]);
-      const float mean = __fdiv_rn(sum, static_cast<float>(C));
-      float ss = 0.f;
+        for (int c = 0; c < NV; ++c)
+          if (c < C) sum = __fadd_rn(sum, v[c]);
+        const float mean = __fdiv_rn(sum, static_cast<float>(C));
+        float ss = 0.f;
 #pragma unroll
-      for (int c = 0; c < SCV_MAX_BANDS; ++c)
-        if (c < C) {
-          const float d = __fsub_rn(v[c], mean);
-          ss = __fadd_rn(ss, __fmul_rn(d, d));
-        }
-      const float den = __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, static_cast<float>(C)), p.div[0]));
+        for (int c = 0; c < NV; ++c)
+          if (c < C) {
+            const float d = __fsub_rn(v[c], mean);
+            ss = __fadd_rn(ss, __fmul_rn(d, d));
+          }
+        const float den = __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, static_cast<float>(C)), p.div[0]));
 #pragma unroll
-      for (int c = 0; c < SCV_MAX_BANDS; ++c)
-        if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mean), den);
-    }
-
-    __nv_bfloat16* o = p.out + ((static_cast<size_t>(tile) * p.side + (r0 + rr)) * p.side + x) * p.cpad;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-    for (int k = 0; k < SCV_MAX_BANDS / 8; ++k) {
-      if (k < nchunk) {
-        uint4 w;
-        w.x = pack2(v[8 * k + 0], v[8 * k + 1]);
-        w.y = pack2(v[8 * k + 2], v[8 * k + 3]);
-        w.z = pack2(v[8 * k + 4], v[8 * k + 5]);
-        w.w = pack2(v[8 * k + 6], v[8 * k + 7]);
-        o4[k] = w;
+        for (int c = 0; c < NV; ++c)
+          if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mean), den);
       }
+
+      uint4* o4 = reinterpret_cast<uint4*>(orow + static_cast<size_t>(x) * p.cpad);
+#pragma unroll
+      for (int k = 0; k < NV / 8; ++k) {
+        if (k < nchunk) {
+          uint4 w;
+          w.x = pack2(v[8 * k + 0], v[8 * k + 1]);
+          w.y = pack2(v[8 * k + 2], v[8 * k + 3]);
+          w.z = pack2(v[8 * k + 4], v[8 * k + 5]);
+          w.w = pack2(v[8 * k + 6], v[8 * k + 7]);
+          o4[k] = w;
+        }
+      }
+      for (int k = NV / 8; k < nchunk; ++k) o4[k] = make_uint4(0, 0, 0, 0);
     }
-    for (int k = SCV_MAX_BANDS / 8; k < nchunk; ++k) o4[k] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -343,18 +372,42 @@ size_t extract_smem_bytes(const ExtractParams& p) {
   return static_cast<size_t>(p.rows_per_block) * ((row_bytes + 16 + 15) & ~15);
 }
 
-cudaError_t launch_extract(const ExtractParams& p, cudaStream_t s) {
-  if (p.n_tiles <= 0) return cudaSuccess;
+template <int DT, int CT>
+static cudaError_t launch_extract_tc(const ExtractParams& p, cudaStream_t s) {
   const size_t smem = extract_smem_bytes(p);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e =
+        cudaFuncSetAttribute(extract_kernel<DT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   dim3 grid((p.side + p.rows_per_block - 1) / p.rows_per_block, p.n_tiles);
-  extract_kernel<<<grid, 256, smem, s>>>(p);
+  extract_kernel<DT, CT><<<grid, 256, smem, s>>>(p);
   return cudaGetLastError();
+}
+template <int DT>
+static cudaError_t launch_extract_t(const ExtractParams& p, cudaStream_t s) {
+  switch (p.C) {  // the band counts of the reference's models: Sentinel-2 (6), NAIP (3 / 4)
+    case 6: return launch_extract_tc<DT, 6>(p, s);
+    case 4: return launch_extract_tc<DT, 4>(p, s);
+    case 3: return launch_extract_tc<DT, 3>(p, s);
+    default: return launch_extract_tc<DT, 0>(p, s);
+  }
+}
+
+cudaError_t launch_extract(const ExtractParams& pin, cudaStream_t s) {
+  if (pin.n_tiles <= 0) return cudaSuccess;
+  ExtractParams p = pin;
+  for (int c = 0; c < SCV_MAX_BANDS; ++c) p.rdiv[c] = 1.0f / p.div[c];  // fp32 RN reciprocal (host IEEE division)
+  switch (p.dtype) {
+    case SCV_U8: return launch_extract_t<SCV_U8>(p, s);
+    case SCV_U16: return launch_extract_t<SCV_U16>(p, s);
+    case SCV_I16: return launch_extract_t<SCV_I16>(p, s);
+    case SCV_F32: return launch_extract_t<SCV_F32>(p, s);
+    case SCV_F64: return launch_extract_t<SCV_F64>(p, s);
+  }
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_tile_stats(const TileStatsParams& p, int n_tiles, cudaStream_t s) {

@@ -28,6 +28,7 @@ struct ExtractParams {
   int norm_mode;
   float sub[SCV_MAX_BANDS];
   float div[SCV_MAX_BANDS];
+  float rdiv[SCV_MAX_BANDS];  // filled by launch_extract: RN(1 / div)
   const float* tile_stats;   // SCV_NORM_TILE_*: per tile, per band (sub, div)
   __nv_bfloat16* out;        // n_tiles * side * side * cpad
 };
