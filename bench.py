@@ -129,16 +129,6 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def split_rows(nrows, world):
-    base, extra = divmod(nrows, world)
-    out, r = [], 0
-    for i in range(world):
-        n = base + (1 if i < extra else 0)
-        out.append((r, r + n))
-        r += n
-    return out
-
-
 def cpu_reference_sample(n_tiles, seed=1, variant='A'):
     """The reference algorithm (generate_chip_indices + per-tile batch-1 predict + crop/stitch) on the
     host cores via the oracle port; returns (MP/s in scene-equivalent pixels, description, cores)."""
@@ -203,6 +193,7 @@ def main():
     ap.add_argument('--ref-tiles', type=int, default=24)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-layers', action='store_true')
+    ap.add_argument('--gather', action='store_true', help='also time the optional NCCL gather of the bands to rank 0')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -237,14 +228,15 @@ def main():
     if args.profile_layers:
         model.set_option('profile_layers', 1)
 
-    # chip grid and this rank's tile rows
+    # chip grid and this rank's tile rows (row-band sharding, no data-path collective)
+    from satellite_computervision_b200 import sharding
     half, side = BUFF // 2, KERNEL + BUFF
-    ys = list(range(half, H - side, KERNEL))
-    xs = list(range(half, W - side, KERNEL))
-    r0, r1 = split_rows(len(ys), world)[rank]
+    ys, xs = sharding.chip_grid(H, W, KERNEL, BUFF)
+    band_info = sharding.rank_band(H, W, KERNEL, BUFF, rank, world)
+    r0, r1 = band_info.tile_row_begin, band_info.tile_row_end
     n_chips_total = len(ys) * len(xs)
-    src_row0, src_row1 = ys[r0] - half, ys[r1 - 1] - half + side
-    dst_row0, dst_rows = ys[r0], (r1 - r0) * KERNEL
+    src_row0, src_row1 = band_info.src_row0, band_info.src_row1
+    dst_row0, dst_rows = band_info.dst_row0, band_info.dst_row1 - band_info.dst_row0
 
     # every rank generates the same scene and keeps its band (pinned host memory for the e2e leg)
     scene = make_scene(H, W, seed=1)
@@ -317,6 +309,17 @@ def main():
         dist.all_reduce(tot)
         h2d, d2h = int(tot[0].item()), int(tot[1].item())
 
+    gather_ms = None
+    if args.gather and world > 1:
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = sharding.gather_mosaic(d_prob, band_info, H, W, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = sharding.max_over_ranks(g0.elapsed_time(g1), device='cuda')
+        del full
+
     if rank == 0:
         pk = peaks()
         n_my = (r1 - r0) * len(xs)
@@ -355,6 +358,8 @@ def main():
                                 'frac': st_gbs / pk['hbm'], 'ms': times['stitch_ms']},
             'stage_ms_last_step_rank0': {k: times[k] for k in ('total_ms', 'extract_ms', 'network_ms', 'stitch_ms')},
         }
+        if gather_ms is not None:
+            line['optional_gather_ms'] = gather_ms
         if args.profile_layers:
             line['layers'] = [{'name': n, 'ms': m, 'tflops': (f * n_my / (m / 1e3) / 1e12 if m > 0 else None)}
                               for n, m, f in zip(layer_names(model), times['layer_ms'], times['layer_flops'])]
