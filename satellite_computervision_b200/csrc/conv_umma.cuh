@@ -49,6 +49,7 @@ struct ConvParams {
   int ncls;
   float* logits;        // N*H*W*ncls fp32
   // persistent slab kernel
+  int n_in_off;         // image offset added to the A-operand TMA coordinate (layer input is a slice of a larger tensor)
   int nslab;            // slab ring depth
   int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kConvThreads)
       uint8_t* a_dst = tiles + static_cast<size_t>(s) * STAGE_BYTES;
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_4d(a_dst, &tmA, &full_bar[s], ch * KC, x0 + dx, y0 + dy, n0);
+        tma_load_4d(a_dst, &tmA, &full_bar[s], ch * KC, x0 + dx, y0 + dy, n0 + p.n_in_off);
         tma_load_2d(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + ch * KC, nb0);
       }
       __syncwarp();
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
         if (elect_one()) {
           mbar_arrive_expect_tx(&slab_full[s], SLAB_BYTES);
           tma_load_4d(slabs + static_cast<size_t>(s) * SLAB_STRIDE, &tmA, &slab_full[s], ch * KC, tx * 8 - HALO,
-                      ty * 16 - HALO, n);
+                      ty * 16 - HALO, n + p.n_in_off);
         }
         __syncwarp();
       }

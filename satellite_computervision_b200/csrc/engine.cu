@@ -435,10 +435,15 @@ struct scv_engine {
   size_t tile_probs_bytes = 0;
   int32_t* d_tile_classes = nullptr;
   size_t tile_classes_bytes = 0;
+  // super-batch tensors shared by every plan: K1 output (layer-0 input) and head logits for up to tile_cap tiles
+  __nv_bfloat16* d_x0_all = nullptr;
+  float* d_logits_all = nullptr;
+  int tile_cap = 0, tile_cap_side = 0;
   // options
   int opt_profile_layers = 0;
   int opt_stages = 0;
   int opt_watchdog_ms = 2000;
+  int opt_super_tiles = 448;  // target tiles per K1 / K4 launch
   // timing
   std::vector<cudaEvent_t> ev_pool;
   struct BatchEv {
@@ -649,7 +654,8 @@ static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* 
 }
 
 static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int in_pitch, int B, int h, int w,
-                       ConvLaunch* L) {
+                       ConvLaunch* L, int n_in = 0) {
+  if (n_in <= 0) n_in = B;  // images in the input tensor (>= B when the input is a slice of a larger tensor)
   memset(L, 0, sizeof *L);
   ConvParams& p = L->p;
   p.N = B;
@@ -687,7 +693,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     L->smem = slab_smem_bytes(l.KC, bn, p.ntaps, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1, nacc);
     if (l.BN != bn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, p.ntaps * l.cin_pad, l.ntotal, l.KC, bn));
     else L->tmB = l.tmB;
-    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, sw, sh, 1));
+    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, sw, sh, 1));
     return SCV_OK;
   }
   L->slab = 0;
@@ -702,7 +708,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   L->grid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
   L->tmB = l.tmB;
   L->smem = conv_smem_bytes(l.KC, l.BN, p.nstage, l.epi, e ? e->arch.cfg.nclasses : 1);
-  SCV_TRY(make_act_tmap(&L->tmA, in_ptr, B, h, w, in_pitch, l.KC, p.TW, p.TH, p.TN));
+  SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, p.TW, p.TH, p.TN));
   return SCV_OK;
 }
 
@@ -742,18 +748,25 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
   size_t total = 0;
   for (size_t i = 0; i < a.bufs.size(); ++i) {
     const BufDef& b = a.bufs[i];
-    const size_t bytes = (size_t)B * (H >> b.level) * (W >> b.level) * b.channels * (b.f32 ? 4 : 2);
+    size_t bytes = (size_t)B * (H >> b.level) * (W >> b.level) * b.channels * (b.f32 ? 4 : 2);
+    if ((int)i == a.x0_buf || (int)i == a.logits_buf) bytes = 0;  // live in the engine's super-batch tensors
     off[i] = total;
     total += (bytes + 1023) & ~size_t(1023);
   }
-  CUDA_TRY(cudaMalloc(&pl->arena, total));
+  CUDA_TRY(cudaMalloc(&pl->arena, std::max<size_t>(total, 1024)));
   pl->arena_bytes = total;
   pl->buf_ptr.resize(a.bufs.size());
   for (size_t i = 0; i < a.bufs.size(); ++i) pl->buf_ptr[i] = pl->arena + off[i];
+  if (!e->d_x0_all || e->tile_cap < B || e->tile_cap_side != H)
+    return fail(SCV_ERR_STATE, "internal: super-batch tensors not sized before planning");
+  pl->buf_ptr[a.x0_buf] = e->d_x0_all;
+  pl->buf_ptr[a.logits_buf] = e->d_logits_all;
   for (auto& l : a.layers) {
     ConvLaunch Ln;
     const int h = H >> l.level, w = W >> l.level;
-    SCV_TRY(fill_launch(e, l, pl->buf_ptr[l.in_buf], a.bufs[l.in_buf].channels, B, h, w, &Ln));
+    // the layer that reads x0 sees the whole super-batch tensor (tile_cap images) and is offset per launch
+    const int n_in = l.in_buf == a.x0_buf ? e->tile_cap : B;
+    SCV_TRY(fill_launch(e, l, pl->buf_ptr[l.in_buf], a.bufs[l.in_buf].channels, B, h, w, &Ln, n_in));
     ConvParams& p = Ln.p;
     if (l.epi == EPI_HEAD) {
       p.head_w = e->d_head_w;
@@ -799,12 +812,18 @@ static void reset_timing(scv_engine* e) {
   e->times_pending = false;
 }
 
-static int run_layers(scv_engine* e, Plan* pl, cudaStream_t s, scv_engine::BatchEv* bev) {
+// Launches the network for `pl->B` tiles whose K1 output starts at image `tile_off` of the super-batch tensors.
+static int run_layers(scv_engine* e, Plan* pl, int tile_off, int side, cudaStream_t s, scv_engine::BatchEv* bev) {
+  const Arch& a = e->arch;
   for (size_t i = 0; i < pl->launches.size(); ++i) {
     if (e->opt_profile_layers && bev) bev->layer_ev.push_back(new_event(e, s));
-    cudaError_t err = conv_launch(pl->launches[i], s);
+    ConvLaunch L = pl->launches[i];
+    const LayerDef& l = a.layers[i];
+    if (l.in_buf == a.x0_buf) L.p.n_in_off = tile_off;
+    if (l.epi == EPI_HEAD) L.p.logits = e->d_logits_all + (size_t)tile_off * side * side * a.cfg.nclasses;
+    cudaError_t err = conv_launch(L, s);
     if (err != cudaSuccess)
-      return fail(SCV_ERR_CUDA, "launch of layer %s failed: %s", e->arch.layers[i].name.c_str(), cudaGetErrorString(err));
+      return fail(SCV_ERR_CUDA, "launch of layer %s failed: %s", l.name.c_str(), cudaGetErrorString(err));
     e->n_launches++;
   }
   if (e->opt_profile_layers && bev) bev->layer_ev.push_back(new_event(e, s));
@@ -834,10 +853,12 @@ static int finalize_times(scv_engine* e) {
       cudaEventElapsedTime(&ms, e->ev_pool[b.e2], e->ev_pool[b.e3]);
       t.stitch_ms += ms;
       t.n_tiles += b.ntiles;
-      for (size_t i = 0; i + 1 < b.layer_ev.size() && i < SCV_MAX_LAYERS; ++i) {
-        cudaEventElapsedTime(&ms, e->ev_pool[b.layer_ev[i]], e->ev_pool[b.layer_ev[i + 1]]);
-        t.layer_ms[i] += ms;
-      }
+      const size_t per = e->arch.layers.size() + 1;  // events per network pass
+      for (size_t k = 0; k + per <= b.layer_ev.size(); k += per)
+        for (size_t i = 0; i + 1 < per && i < SCV_MAX_LAYERS; ++i) {
+          cudaEventElapsedTime(&ms, e->ev_pool[b.layer_ev[k + i]], e->ev_pool[b.layer_ev[k + i + 1]]);
+          t.layer_ms[i] += ms;
+        }
     }
     t.n_batches = (int)e->batch_ev.size();
   }
@@ -885,14 +906,38 @@ static int norm_to_params(const scv_norm* n, int C, ExtractParams* ep) {
   return SCV_OK;
 }
 
-// Runs tiles [t0, t0+nb) of the job through extract -> network -> stitch/head on `s`.
-static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStream_t s) {
-  Plan* pl = nullptr;
-  SCV_TRY(get_plan(e, nb, job.side, job.side, &pl));
+// (Re)sizes the super-batch tensors; plans bake their addresses into tensor maps, so growing drops the plans.
+static int ensure_tile_tensors(scv_engine* e, int ntiles, int side) {
+  if (e->d_x0_all && e->tile_cap >= ntiles && e->tile_cap_side == side) return SCV_OK;
+  const int cap = std::max(ntiles, e->tile_cap_side == side ? e->tile_cap : 0);
+  CUDA_TRY(cudaDeviceSynchronize());  // callers may be on a user stream
+  for (auto& pl : e->plans) cudaFree(pl->arena);
+  e->plans.clear();
+  cudaFree(e->d_x0_all);
+  cudaFree(e->d_logits_all);
+  e->d_x0_all = nullptr;
+  e->d_logits_all = nullptr;
+  e->tile_cap = 0;
+  const size_t px = (size_t)cap * side * side;
+  CUDA_TRY(cudaMalloc(&e->d_x0_all, px * e->arch.c0pad * 2));
+  CUDA_TRY(cudaMalloc(&e->d_logits_all, px * e->arch.cfg.nclasses * 4));
+  e->tile_cap = cap;
+  e->tile_cap_side = side;
+  return SCV_OK;
+}
+
+// Runs tiles [t0, t0+n) of the job as ONE super-batch on `s`: one K1 launch for all of them, the network in
+// device batches of `sizes`, one K4 launch for all of them (the HBM-bound kernels need launches long enough to
+// reach bandwidth; the conv kernels need batches small enough for the activation arena).
+static int run_super(scv_engine* e, const TileJob& job, int t0, const std::vector<int>& sizes, cudaStream_t s) {
+  int n = 0;
+  for (int nb : sizes) n += nb;
+  if (n == 0) return SCV_OK;
+  SCV_TRY(ensure_tile_tensors(e, n, job.side));
   e->last_side = job.side;
   Arch& a = e->arch;
   scv_engine::BatchEv bev{};
-  bev.ntiles = nb;
+  bev.ntiles = n;
   bev.e0 = new_event(e, s);
 
   ExtractParams ep{};
@@ -903,15 +948,15 @@ static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStre
   ep.C = job.C;
   ep.src_row0 = job.src_row0;
   ep.origins = job.d_src_origins + t0;
-  ep.n_tiles = nb;
+  ep.n_tiles = n;
   ep.side = job.side;
   ep.cpad = a.c0pad;
   SCV_TRY(norm_to_params(job.norm, job.C, &ep));
   const int row_bytes = job.side * job.C * dtype_bytes(job.dtype);
   ep.rows_per_block = std::max(1, std::min(8, (44 * 1024) / (row_bytes + 32)));
-  ep.out = (__nv_bfloat16*)pl->buf_ptr[a.x0_buf];
+  ep.out = e->d_x0_all;
   if (ep.norm_mode == SCV_NORM_TILE_ZSCORE || ep.norm_mode == SCV_NORM_TILE_MINMAX) {
-    SCV_TRY(ensure((void**)&e->d_tile_stats, &e->tile_stats_cap, (size_t)nb * job.C * 2 * sizeof(float)));
+    SCV_TRY(ensure((void**)&e->d_tile_stats, &e->tile_stats_cap, (size_t)n * job.C * 2 * sizeof(float)));
     TileStatsParams sp{};
     sp.src = ep.src;
     sp.dtype = job.dtype;
@@ -923,7 +968,7 @@ static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStre
     sp.mode = ep.norm_mode;
     sp.eps = ep.div[0];
     sp.stats = e->d_tile_stats;
-    CUDA_TRY(launch_tile_stats(sp, nb, s));
+    CUDA_TRY(launch_tile_stats(sp, n, s));
     e->n_launches++;
     ep.tile_stats = e->d_tile_stats;
   }
@@ -932,13 +977,18 @@ static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStre
   e->n_launches++;
   bev.e1 = new_event(e, s);
 
-  SCV_TRY(run_layers(e, pl, s, &bev));
+  int off = 0;
+  for (int nb : sizes) {
+    Plan* pl = nullptr;
+    SCV_TRY(get_plan(e, nb, job.side, job.side, &pl));
+    SCV_TRY(run_layers(e, pl, off, job.side, s, &bev));
+    off += nb;
+  }
   bev.e2 = new_event(e, s);
 
-  const float* logits = (const float*)pl->buf_ptr[a.logits_buf];
   if (job.d_dst_origins) {
     StitchParams sp{};
-    sp.logits = logits;
+    sp.logits = e->d_logits_all;
     sp.side = job.side;
     sp.ncls = a.cfg.nclasses;
     sp.head = a.cfg.head;
@@ -952,11 +1002,11 @@ static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStre
     sp.out_W = job.out_W;
     sp.prob = job.d_prob;
     sp.mask = job.d_mask;
-    CUDA_TRY(launch_stitch(sp, nb, s));
+    CUDA_TRY(launch_stitch(sp, n, s));
   } else {
     HeadTilesParams hp{};
-    hp.logits = logits;
-    hp.npix = (long long)nb * job.side * job.side;
+    hp.logits = e->d_logits_all;
+    hp.npix = (long long)n * job.side * job.side;
     hp.ncls = a.cfg.nclasses;
     hp.head = a.cfg.head;
     hp.threshold = a.cfg.threshold;
@@ -971,12 +1021,31 @@ static int run_batch(scv_engine* e, const TileJob& job, int t0, int nb, cudaStre
   return SCV_OK;
 }
 
+// Groups the balanced device batches of `n` tiles into super-batches of roughly `target` tiles.
+static void super_batches(int n, int maxb, int target, std::vector<std::vector<int>>* out);
+
 static void balanced_batches(int n, int maxb, std::vector<int>* sizes) {
   sizes->clear();
   if (n <= 0) return;
   const int nb = (n + maxb - 1) / maxb;
   const int base = n / nb, extra = n % nb;
   for (int i = 0; i < nb; ++i) sizes->push_back(base + (i < extra ? 1 : 0));
+}
+
+static void super_batches(int n, int maxb, int target, std::vector<std::vector<int>>* out) {
+  std::vector<int> sizes;
+  balanced_batches(n, maxb, &sizes);
+  out->clear();
+  if (sizes.empty()) return;
+  const int per = std::max(1, (target + sizes[0] - 1) / sizes[0]);          // device batches per super-batch
+  const int nsuper = ((int)sizes.size() + per - 1) / per;
+  const int base = (int)sizes.size() / nsuper, extra = (int)sizes.size() % nsuper;
+  size_t k = 0;
+  for (int i = 0; i < nsuper; ++i) {
+    const int cnt = base + (i < extra ? 1 : 0);
+    out->emplace_back(sizes.begin() + k, sizes.begin() + k + cnt);
+    k += cnt;
+  }
 }
 
 // generate_chip_indices (utils/prediction_tools.py:87-109): y in range(buff/2, H-(buff+kernel), kernel)
@@ -1080,6 +1149,8 @@ void scv_engine_destroy(scv_engine* e) {
   cudaFree(e->d_stage);
   cudaFree(e->d_tile_probs);
   cudaFree(e->d_tile_classes);
+  cudaFree(e->d_x0_all);
+  cudaFree(e->d_logits_all);
   cudaStreamDestroy(e->stream);
   cudaStreamDestroy(e->h2d);
   cudaStreamDestroy(e->d2h);
@@ -1118,6 +1189,7 @@ int scv_set_option(scv_engine* e, const char* key, int value) {
     e->plans.clear();
   } else if (k == "watchdog_ms") e->opt_watchdog_ms = value;
   else if (k == "max_batch") e->arch.cfg.max_batch = std::max(1, value);
+  else if (k == "super_tiles") e->opt_super_tiles = std::max(1, value);
   else return fail(SCV_ERR_INVALID, "unknown option '%s'", key);
   return SCV_OK;
 }
@@ -1208,12 +1280,12 @@ int scv_predict_mosaic_device(scv_engine* e, const void* d_hwc, int dtype, int H
   job.force_scalar = force_scalar;
   job.d_prob = d_prob;
   job.d_mask = d_mask;
-  std::vector<int> sizes;
-  balanced_batches(n, e->arch.cfg.max_batch, &sizes);
+  std::vector<std::vector<int>> supers;
+  super_batches(n, e->arch.cfg.max_batch, e->opt_super_tiles, &supers);
   int t0 = 0;
-  for (int nb : sizes) {
-    SCV_TRY(run_batch(e, job, t0, nb, s));
-    t0 += nb;
+  for (auto& sizes : supers) {
+    SCV_TRY(run_super(e, job, t0, sizes, s));
+    for (int nb : sizes) t0 += nb;
   }
   if (!stream) {
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -1299,16 +1371,18 @@ int scv_predict_mosaic(scv_engine* e, const void* hwc, int dtype, int H, int W, 
   job.d_prob = e->d_prob;
   job.d_mask = out_mask ? e->d_mask : nullptr;
 
-  std::vector<int> sizes;
-  balanced_batches(n, e->arch.cfg.max_batch, &sizes);
+  std::vector<std::vector<int>> supers;
+  super_batches(n, e->arch.cfg.max_batch, e->opt_super_tiles, &supers);
   int t0 = 0, rows_downloaded = 0, rows_waited = 0;
   int rc = SCV_OK;
   const size_t core_w = (size_t)ncols * K;
-  for (int nb : sizes) {
-    const int last_tile_row = (t0 + nb - 1) / ncols;  // relative tile row this batch reaches
+  for (auto& sizes : supers) {
+    int nsup = 0;
+    for (int nb : sizes) nsup += nb;
+    const int last_tile_row = (t0 + nsup - 1) / ncols;  // relative tile row this super-batch reaches
     for (; rows_waited <= last_tile_row; ++rows_waited) cudaStreamWaitEvent(e->stream, up_ev[rows_waited], 0);
-    if ((rc = run_batch(e, job, t0, nb, e->stream)) != SCV_OK) break;
-    t0 += nb;
+    if ((rc = run_super(e, job, t0, sizes, e->stream)) != SCV_OK) break;
+    t0 += nsup;
     // D2H of the tile rows completed so far (cores only: columns [xs[0], xs[0]+ncols*K))
     const int complete = t0 / ncols;
     if (complete > rows_downloaded) {
@@ -1372,7 +1446,7 @@ static int run_stacked(scv_engine* e, const void* nhwc, int dtype, int N, int H,
     // run_batch offsets origin arrays and per-tile outputs by t0: compensate for the per-batch staging
     TileJob bj = job;
     bj.d_src_origins = e->d_origins - t0;
-    SCV_TRY(run_batch(e, bj, t0, nb, e->stream));
+    SCV_TRY(run_super(e, bj, t0, std::vector<int>{nb}, e->stream));
     if (h_probs)
       CUDA_TRY(cudaMemcpyAsync(h_probs + (size_t)t0 * tile_px * ncls, e->d_tile_probs + (size_t)t0 * tile_px * ncls,
                                (size_t)nb * tile_px * ncls * 4, cudaMemcpyDeviceToHost, e->stream));
