@@ -82,7 +82,51 @@ cudaError_t attr_bn() {
 }
 }  // namespace
 
+// KC == 8 exists only as the slab kernel of a 3x3 first layer (EPI_STORE / EPI_POOL_SKIP).
+template <int BN>
+cudaError_t launch_kc8(const ConvLaunch& L, cudaStream_t s) {
+  if (!L.slab || L.p.ntaps != 9) return cudaErrorInvalidValue;
+  if constexpr (slab_nacc_ok(BN, 4)) {
+    if (L.nacc == 4) {
+      if (L.EPI == EPI_STORE)
+        conv_slab_kernel<8, BN, EPI_STORE, 9, 4><<<L.grid, slab_threads(4), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+      else if (L.EPI == EPI_POOL_SKIP)
+        conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 4><<<L.grid, slab_threads(4), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+      else
+        return cudaErrorInvalidValue;
+      return cudaGetLastError();
+    }
+  }
+  if (L.EPI == EPI_STORE)
+    conv_slab_kernel<8, BN, EPI_STORE, 9, 2><<<L.grid, slab_threads(2), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+  else if (L.EPI == EPI_POOL_SKIP)
+    conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 2><<<L.grid, slab_threads(2), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+template <int BN>
+cudaError_t attr_kc8() {
+  const int kMax = 227 * 1024;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(conv_slab_kernel<8, BN, EPI_STORE, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+  if constexpr (slab_nacc_ok(BN, 4)) {
+    if ((e = cudaFuncSetAttribute(conv_slab_kernel<8, BN, EPI_STORE, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.KC == 8) {
+    switch (L.BN) {
+      case 32: return launch_kc8<32>(L, stream);
+      case 64: return launch_kc8<64>(L, stream);
+      case 128: return launch_kc8<128>(L, stream);
+    }
+    return cudaErrorInvalidValue;
+  }
   switch (L.KC) {
     case 16: return launch_bn<16>(L, stream);
     case 32: return launch_bn<32>(L, stream);
@@ -95,6 +139,9 @@ cudaError_t conv_init_attributes() {
   static bool done = false;
   if (done) return cudaSuccess;
   cudaError_t e;
+  if ((e = attr_kc8<32>()) != cudaSuccess) return e;
+  if ((e = attr_kc8<64>()) != cudaSuccess) return e;
+  if ((e = attr_kc8<128>()) != cudaSuccess) return e;
   if ((e = attr_bn<16>()) != cudaSuccess) return e;
   if ((e = attr_bn<32>()) != cudaSuccess) return e;
   if ((e = attr_bn<64>()) != cudaSuccess) return e;

@@ -527,8 +527,10 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int chunks = p.Cin / KC;
-  const int nwt = NTAPS * chunks;
+  // KC == 8 (first layer, 8 stored input channels): rows are 16 B, no swizzle; two taps form one K = 16 step
+  // (the descriptor's leading-byte-offset is the distance between the two taps' windows), K = 9*8 -> 80.
+  const int chunks = KC == 8 ? 1 : p.Cin / KC;
+  const int nwt = KC == 8 ? 10 : NTAPS * chunks;
   const int nslab = p.nslab;
   uint8_t* w_smem = base;
   uint8_t* slabs = base + static_cast<size_t>(nwt) * WT_BYTES;
@@ -589,10 +591,15 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, static_cast<uint32_t>(nwt) * WT_BYTES);
-      for (int ch = 0; ch < chunks; ++ch)
-        for (int tap = 0; tap < NTAPS; ++tap)  // smem order [chunk][tap]; global K index = tap*Cin + ch*KC
-          tma_load_2d(w_smem + static_cast<size_t>(ch * NTAPS + tap) * WT_BYTES, &tmB, w_full, tap * p.Cin + ch * KC,
-                      nb0);
+      if constexpr (KC == 8) {
+        for (int i = 0; i < 10; ++i)  // ten 8-wide K slices (nine taps + one all-zero slice), [BN rows][16 B] each
+          tma_load_2d(w_smem + static_cast<size_t>(i) * WT_BYTES, &tmB, w_full, i * 8, nb0);
+      } else {
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int tap = 0; tap < NTAPS; ++tap)  // smem order [chunk][tap]; global K index = tap*Cin + ch*KC
+            tma_load_2d(w_smem + static_cast<size_t>(ch * NTAPS + tap) * WT_BYTES, &tmB, w_full,
+                        tap * p.Cin + ch * KC, nb0);
+      }
     }
     __syncwarp();
     uint32_t it = 0;
@@ -640,15 +647,26 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
         }
         tc_fence_after();
         const uint32_t slab_addr = smem_u32(slabs + static_cast<size_t>(s) * SLAB_STRIDE);
+        if constexpr (KC == 8) {
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {  // tap pair (2j, 2j+1); the last pair re-reads tap 8 against zero weights
+              const int t0 = 2 * j, t1 = j < 4 ? 2 * j + 1 : 8;
+              const int o0 = (t0 / 3) * SW + t0 % 3, o1 = (t1 / 3) * SW + t1 % 3;  // window offsets in pixels
+              const uint64_t da = umma_smem_desc_nosw(slab_addr + o0 * 16, (o1 - o0) * 16, SW * 16);
+              const uint64_t db = umma_smem_desc_nosw(w_addr + t0 * WT_BYTES, WT_BYTES, 128);
+              umma_bf16(tacc, da, db, IDESC, j != 0 ? 1u : 0u);
+            }
+            umma_commit(&slab_empty[s]);
+          }
+          __syncwarp();
+          continue;
+        }
         const uint64_t da0 = umma_smem_desc_sbo(slab_addr, ROWB, SW * ROWB);
         const uint64_t db0 = umma_smem_desc(w_addr + static_cast<uint32_t>(ch * NTAPS) * WT_BYTES, ROWB);
         if (elect_one()) {
 #pragma unroll
-#if defined(SCV_DBG_ONE_MMA)  // timing experiment hook (results are wrong when defined)
-          for (int tap = 0; tap < 1; ++tap) {
-#else
           for (int tap = 0; tap < NTAPS; ++tap) {
-#endif
             const int dy = NTAPS == 9 ? tap / 3 : 0;
             const int dx = NTAPS == 9 ? tap % 3 : 0;
 #pragma unroll
@@ -714,9 +732,12 @@ __host__ __device__ inline int slab_stride_bytes(int KC, int ntaps) {
 __host__ __device__ inline size_t slab_stage_bytes(int epi, int nacc) {
   return static_cast<size_t>(4 * nacc) * slab_stage_warp_bytes(epi);
 }
+__host__ __device__ inline size_t slab_weight_bytes(int KC, int BN, int ntaps, int cin) {
+  return KC == 8 ? static_cast<size_t>(10) * BN * 16 : static_cast<size_t>(ntaps) * cin * BN * 2;
+}
 __host__ __device__ inline size_t slab_smem_bytes(int KC, int BN, int ntaps, int cin, int nslab, int epi, int ncls,
                                                   int nacc) {
-  size_t s = 1024 + static_cast<size_t>(ntaps) * (cin / KC) * BN * KC * 2 +
+  size_t s = 1024 + slab_weight_bytes(KC, BN, ntaps, cin) +
              static_cast<size_t>(nslab) * slab_stride_bytes(KC, ntaps) + slab_stage_bytes(epi, nacc);
   s += (2 * nslab + 2 * 4 + 1) * 8 + 16;
   s += BN * 4;

@@ -60,7 +60,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 static CUtensorMapSwizzle swizzle_for(int kc) {
-  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : (kc == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
 }
 
 // bf16 NHWC activation tensor (N,H,W,Cpitch) viewed as 4-D (C, W, H, N); box (KC, TW, TH, TN).
@@ -130,11 +131,14 @@ static int make_convt_store_tmap(CUtensorMap* tm, const void* ptr, int N, int H,
 
 // ============================================================== architecture
 static int pad_channels(int c) {
+  if (c <= 8) return 8;  // one pixel = one 16-byte store; first layer runs the KC == 8 no-swizzle slab path
   if (c <= 16) return 16;
   if (c <= 32) return 32;
   return (c + 63) / 64 * 64;
 }
-static int kc_for(int cpad) { return cpad <= 16 ? 16 : (cpad <= 32 ? 32 : 64); }
+static int kc_for(int cpad) { return cpad <= 8 ? 8 : (cpad <= 16 ? 16 : (cpad <= 32 ? 32 : 64)); }
+// K extent of a layer's weight matrix: taps * Cin_pad, except the 8-channel first layer (9 taps -> ten 8-wide slices)
+static size_t k_total(int kc, int ntaps, int cin_pad) { return kc == 8 ? 80 : (size_t)ntaps * cin_pad; }
 static int bn_for(int ntotal) {
   for (int bn : {256, 128, 64, 32})
     if (ntotal % bn == 0) return bn;
@@ -495,7 +499,7 @@ static const float BN_EPS = 1e-3f;  // keras BatchNormalization default
 static int upload_layer(LayerDef& l, const std::vector<float>& w /*[ntotal][ktotal]*/, const std::vector<float>& bias,
                         const std::vector<float>* skip_s, const std::vector<float>* skip_t) {
   const int ntaps = l.kind == L_CONV3 ? 9 : 1;
-  const size_t ktotal = (size_t)ntaps * l.cin_pad;
+  const size_t ktotal = k_total(l.KC, ntaps, l.cin_pad);
   std::vector<__nv_bfloat16> wb(w.size());
   for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2bfloat16_rn(w[i]);
   if (l.d_w) cudaFree(l.d_w);
@@ -534,7 +538,7 @@ static int fold_and_upload(scv_engine* e, const scv_tensor* t) {
   Arch& a = e->arch;
   for (auto& l : a.layers) {
     const int ntaps = l.kind == L_CONV3 ? 9 : 1;
-    const size_t ktotal = (size_t)ntaps * l.cin_pad;
+    const size_t ktotal = k_total(l.KC, ntaps, l.cin_pad);
     std::vector<float> w((size_t)l.ntotal * ktotal, 0.f), bias(l.ntotal, 0.f);
     const float* K = t[l.w_kernel].data;
     const float* Bv = t[l.w_bias].data;
@@ -617,11 +621,11 @@ static const size_t kSlabWeightBudget = 150 * 1024;
 static int umma_cycles(int bn) { return bn <= 32 ? 46 : (bn <= 64 ? 54 : (bn <= 128 ? 70 : 134)); }
 
 static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* nslab, int* nacc_out) {
-  if (!env_int("SCV_SLAB", 1)) return false;
+  if (!env_int("SCV_SLAB", 1) && l.KC != 8) return false;
   if (w % 8 || h % 16) return false;
   const int ntaps = l.kind == L_CONV3 ? 9 : 1;
   const long long m_tiles = (long long)B * (h / 16) * (w / 8);
-  const bool force = env_int("SCV_SLAB_FORCE", 0) != 0;
+  const bool force = env_int("SCV_SLAB_FORCE", 0) != 0 || l.KC == 8;  // the 8-channel first layer has no tile-kernel form
   const int slab_stride = slab_stride_bytes(l.KC, ntaps);
   const int chunks = l.cin_pad / l.KC;
   for (int bn : {256, 128, 64, 32}) {
@@ -630,10 +634,10 @@ static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* 
     const int n_tiles_n = l.ntotal / bn;
     // persistent CTAs need enough tiles each, and re-reading A once per N tile must stay cheap
     if (!force && (n_tiles_n > 2 || m_tiles * n_tiles_n < 8LL * sm_count())) continue;
-    const size_t wbytes = (size_t)ntaps * l.cin_pad * bn * 2;
+    const size_t wbytes = slab_weight_bytes(l.KC, bn, ntaps, l.cin_pad);
     if (wbytes > kSlabWeightBudget) continue;
     // epilogue budget: with few MMAs per tile the epilogue warps must turn tiles around fast -> 4 groups
-    const long long mma_cycles = (long long)ntaps * (l.cin_pad / 16) * umma_cycles(bn);
+    const long long mma_cycles = (long long)(k_total(l.KC, ntaps, l.cin_pad) / 16) * umma_cycles(bn);
     const int first = (mma_cycles < 3000 && slab_nacc_ok(bn, 4)) ? 4 : 2;
     for (int nacc : {first, first == 4 ? 2 : 4}) {
       if (!slab_nacc_ok(bn, nacc)) continue;
@@ -691,11 +695,12 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     if (grid > work) grid = (int)work;
     L->grid = std::max(grid, p.n_tiles_n);
     L->smem = slab_smem_bytes(l.KC, bn, p.ntaps, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1, nacc);
-    if (l.BN != bn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, p.ntaps * l.cin_pad, l.ntotal, l.KC, bn));
+    if (l.BN != bn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, p.ntaps, l.cin_pad), l.ntotal, l.KC, bn));
     else L->tmB = l.tmB;
     SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, sw, sh, 1));
     return SCV_OK;
   }
+  if (l.KC == 8) return fail(SCV_ERR_INVALID, "layer %s: 8-channel input needs tile sides that are multiples of 16", l.name.c_str());
   L->slab = 0;
   L->BN = l.BN;
   tile_box(w, &p.TW, &p.TH, &p.TN);
@@ -1549,7 +1554,7 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
   }
   if (l.BN == 0) return fail(SCV_ERR_INVALID, "Cout=%d unsupported (needs a multiple of 32)", Cout);
   const int ntaps = kind == L_CONV3 ? 9 : 1;
-  const size_t ktotal = (size_t)ntaps * l.cin_pad;
+  const size_t ktotal = k_total(l.KC, ntaps, l.cin_pad);
   std::vector<float> w((size_t)l.ntotal * ktotal, 0.f), b(l.ntotal, 0.f);
   if (kind == L_CONV3) {
     for (int tap = 0; tap < 9; ++tap)

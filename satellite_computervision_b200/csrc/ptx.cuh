@@ -201,6 +201,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
   return umma_smem_desc_sbo(saddr, row_bytes, 8 * row_bytes);
 }
 
+// No-swizzle ("interleaved") K-major descriptor: core matrix = 8 rows x 16 B stored contiguously (128 B);
+// `sbo` = byte distance between 8-row groups, `lbo` = byte distance between the two 8-element K halves of a
+// K = 16 step.  (cute: ((8,n),2):((1,SBO),LBO) in 16-byte units, layout type 0.)
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4)                                   // D format: F32
