@@ -119,6 +119,7 @@ cudaError_t attr_kc8() {
 }
 
 cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.slab == 2) return conv_rows_launch(L, stream);
   if (L.KC == 8) {
     switch (L.BN) {
       case 32: return launch_kc8<32>(L, stream);
@@ -145,6 +146,7 @@ cudaError_t conv_init_attributes() {
   if ((e = attr_bn<16>()) != cudaSuccess) return e;
   if ((e = attr_bn<32>()) != cudaSuccess) return e;
   if ((e = attr_bn<64>()) != cudaSuccess) return e;
+  if ((e = conv_rows_init_attributes()) != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
 }

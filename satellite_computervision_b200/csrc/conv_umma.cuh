@@ -53,6 +53,7 @@ struct ConvParams {
   int nslab;            // slab ring depth
   int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
+  int dbg;              // timing experiments only (env SCV_ROWS_DBG; results are wrong when non-zero)
   // watchdog
   int* err;
   unsigned long long watchdog_ns;
@@ -752,7 +753,7 @@ struct ConvLaunch {
   CUtensorMap tmOut, tmPool;  // slab kernel only: TMA-store maps of the bf16 outputs
   ConvParams p;
   int KC, BN, EPI;
-  int slab;  // 1: conv_slab_kernel (persistent), 0: conv_umma_kernel (one tile per CTA)
+  int slab;  // 2: conv_rows_kernel (row streaming, conv_rows.cuh), 1: conv_slab_kernel (persistent), 0: conv_umma_kernel
   int nacc;  // slab kernel: accumulators / epilogue warpgroups (2 or 4)
   int grid;
   size_t smem;
@@ -762,5 +763,8 @@ struct ConvLaunch {
 cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream);
 // Sets the max-dynamic-smem attribute of every instantiation (once per device).
 cudaError_t conv_init_attributes();
+// conv_rows.cu
+cudaError_t conv_rows_launch(const ConvLaunch& L, cudaStream_t stream);
+cudaError_t conv_rows_init_attributes();
 
 }  // namespace scv

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/scv.h"
+#include "conv_rows.cuh"
 #include "conv_umma.cuh"
 #include "tile_kernels.cuh"
 
@@ -657,6 +658,24 @@ static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* 
   return false;
 }
 
+// Row-streaming tap-packed kernel (conv_rows.cuh): 3x3 layers with Cout 32/64 on rows that split into
+// 128-pixel strips.  The choice depends on the layer geometry only -- never on the batch size -- so a
+// tile's result does not depend on how many tiles ran with it.
+static bool plan_rows(const LayerDef& l, int h, int w, int ncls, int* nslab) {
+  if (!env_int("SCV_ROWS", 1)) return false;
+  if (l.kind != L_CONV3 || w % kRowsPx || (h & 1)) return false;
+  if (l.KC != 32 && l.KC != 64) return false;
+  if (l.ntotal != l.cout || (l.cout != 32 && l.cout != 64)) return false;
+  if (l.epi != EPI_STORE && l.epi != EPI_POOL_SKIP && l.epi != EPI_HEAD) return false;
+  const int chunks = l.cin_pad / l.KC;
+  for (int ns = std::max(6, 4 * chunks); ns >= 2 * chunks && ns >= 3; --ns)  // slabs of two input rows each
+    if (rows_smem_bytes(l.KC, l.cout, l.cin_pad, ns, l.epi, ncls) <= kSlabSmemBudget) {
+      *nslab = ns;
+      return true;
+    }
+  return false;
+}
+
 static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int in_pitch, int B, int h, int w,
                        ConvLaunch* L, int n_in = 0) {
   if (n_in <= 0) n_in = B;  // images in the input tensor (>= B when the input is a slice of a larger tensor)
@@ -677,6 +696,28 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   L->KC = l.KC;
   L->EPI = l.epi;
   int bn = 0, ns = 0, nacc = 2;
+  if (plan_rows(l, h, w, e ? e->arch.cfg.nclasses : 1, &ns)) {
+    L->slab = 2;
+    p.dbg = env_int("SCV_ROWS_DBG", 0);
+    L->BN = l.cout;
+    L->nacc = kRowsEpiGroups;
+    p.TW = kRowsPx, p.TH = 1, p.TN = 1;
+    p.tiles_x = w / kRowsPx;
+    p.tiles_y = h;
+    p.tiles_n = B;
+    p.n_tiles_n = 1;
+    p.nslab = ns;
+    // issuers in flight must not exceed the reuse distance (in row pairs) of a slab slot or an accumulator pair
+    p.n_issuers = std::max(1, std::min({kRowsIssuers, ns / (l.cin_pad / l.KC), 256 / l.cout,
+                                        env_int("SCV_ROWS_ISSUERS", kRowsIssuers)}));
+    const long long pairs = (long long)B * p.tiles_x * (h / 2);
+    L->grid = (int)std::min<long long>(sm_count(), pairs);
+    L->smem = rows_smem_bytes(l.KC, l.cout, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1);
+    if (l.BN != l.cout) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, l.cout));
+    else L->tmB = l.tmB;
+    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, kRowsSlabPx, 2, 1));
+    return SCV_OK;
+  }
   if (plan_slab(l, B, h, w, &bn, &ns, &nacc)) {
     L->nacc = nacc;
     const int sw = p.ntaps == 9 ? 10 : 8, sh = p.ntaps == 9 ? 18 : 16;
@@ -722,6 +763,12 @@ static int finish_slab_maps(ConvLaunch* L, const LayerDef& l) {
   if (!L->slab || l.epi == EPI_HEAD) return SCV_OK;
   const ConvParams& p = L->p;
   const int cb = 32;  // kStageRowB / 2 channels per store box
+  if (L->slab == 2) {  // row kernel: one warp stores 32 pixels of two rows
+    SCV_TRY(make_store_tmap(&L->tmOut, p.out, p.N, p.H, p.W, p.out_pitch, cb, 32, 2));
+    if (l.epi == EPI_POOL_SKIP)
+      SCV_TRY(make_store_tmap(&L->tmPool, p.pool_out, p.N, p.H / 2, p.W / 2, p.pool_pitch, cb, 16, 1));
+    return SCV_OK;
+  }
   if (l.epi == EPI_CONVT) return make_convt_store_tmap(&L->tmOut, p.out, p.N, p.H, p.W, p.out_pitch, cb);
   SCV_TRY(make_store_tmap(&L->tmOut, p.out, p.N, p.H, p.W, p.out_pitch, cb, 8, 4));
   if (l.epi == EPI_POOL_SKIP)
@@ -790,7 +837,7 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
       fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,
-              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab ? "slab" : "tile", Ln.KC, Ln.BN,
+              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile"), Ln.KC, Ln.BN,
               Ln.slab ? "nslab" : "nstage", Ln.slab ? Ln.p.nslab : Ln.p.nstage, Ln.slab ? Ln.nacc : 1, Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
@@ -1626,6 +1673,8 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
       Ln.p.nstage = std::max(1, atoi(s));
       Ln.smem = conv_smem_bytes(l.KC, l.BN, Ln.p.nstage, l.epi, 1);
     }
+  if (const char* s = getenv("SCV_DEBUG_GRID"))  // persistent kernels: fewer CTAs -> longer streams per CTA
+    if (Ln.slab && atoi(s) > 0) Ln.grid = std::max(Ln.p.n_tiles_n, std::min(Ln.grid, atoi(s)) / Ln.p.n_tiles_n * Ln.p.n_tiles_n);
   Ln.p.relu = relu;
   Ln.p.out = d_y;
   Ln.p.out_pitch = Cout;

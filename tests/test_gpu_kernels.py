@@ -34,6 +34,64 @@ CONV_CASES = [
 ]
 
 
+# Row-streaming tap-packed kernel (conv_rows.cuh): widths that are multiples of 128, Cout 32 / 64.
+# `grid` caps the number of persistent CTAs so one CTA streams many rows: segment changes, ring wrap
+# (16 row accumulators at Cout 32, 8 at Cout 64) and split UMMAs at the wrap are all exercised.
+ROWS_CASES = [
+    # N, H, W, Cin, Cout, grid
+    (1, 8, 128, 32, 32, 0),
+    (2, 6, 256, 64, 32, 0),
+    (1, 10, 128, 32, 64, 0),
+    (3, 4, 128, 64, 64, 0),
+    (1, 4, 384, 128, 64, 0),      # two channel chunks
+    (2, 40, 128, 32, 32, 1),      # one CTA: 80 rows, two segments, ring wraps 5 times
+    (2, 22, 256, 64, 64, 3),      # uneven split over 3 CTAs: segments start mid-image
+    (1, 36, 128, 128, 32, 2),     # two chunks per row, streaming
+    (3, 18, 128, 16, 64, 2),      # KC=16 is not a row-kernel shape: must still be right (slab / tile path)
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,grid', ROWS_CASES)
+def test_conv3x3_rows_kernel_matches_torch(N, H, W, Cin, Cout, grid, monkeypatch):
+    if grid:
+        monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
+    rng = np.random.default_rng(N * 1000 + H + W + Cin + Cout)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    got = G.conv3x3_device(x, k, b)
+    ref = G.conv3x3_ref(x, k, b)
+    s = G.err_stats(got, ref)
+    print('conv3x3 rows', (N, H, W, Cin, Cout, grid), s)
+    assert s['nan'] == 0 and s['n_bad'] == 0, s
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,grid', [(2, 8, 128, 32, 32, 0), (1, 12, 256, 64, 64, 0), (2, 36, 128, 32, 32, 1),
+                                                 (2, 20, 256, 32, 64, 3)])
+def test_rows_kernel_fused_maxpool(N, H, W, Cin, Cout, grid, monkeypatch):
+    if grid:
+        monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    y, p = G.conv3x3_device(x, k, b, pooled=True)
+    assert G.err_stats(y, G.conv3x3_ref(x, k, b))['n_bad'] == 0
+    assert np.array_equal(p, G.maxpool_ref(y))
+
+
+def test_rows_kernel_equals_slab_kernel_bitwise(monkeypatch):
+    """Same summation order as the 8x16-tile kernels whenever Cin fits one chunk: identical bits."""
+    rng = np.random.default_rng(23)
+    x = rng.standard_normal((2, 16, 128, 64)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, 64, 32)) / 24).astype(np.float32)
+    b = rng.standard_normal(32).astype(np.float32) * 0.1
+    rows = G.conv3x3_device(x, k, b)
+    monkeypatch.setenv('SCV_ROWS', '0')
+    other = G.conv3x3_device(x, k, b)
+    assert np.array_equal(rows, other)
+
+
 @pytest.mark.parametrize('N,H,W,Cin,Cout', CONV_CASES)
 def test_conv3x3_matches_torch(N, H, W, Cin, Cout):
     rng = np.random.default_rng(N * 1000 + H + W + Cin + Cout)

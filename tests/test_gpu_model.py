@@ -35,6 +35,8 @@ def _mk(variant, nch, ncls, filters, seed=0, head_bias=None, head_gain=1.0, **kw
     ('A', 1, (32, 64), 64, 3),
     ('B', 2, (32, 64), 64, 2),
     ('A', 1, (32, 64, 128), 96, 2),
+    ('A', 1, (32, 64), 128, 2),                  # 128-wide level 0: row-streaming kernel (pool, store, head epilogues)
+    ('B', 2, (32, 64), 256, 1),                  # two strips per row, softmax head through the generic head epilogue
     ('B', 3, (32, 64, 128, 256, 512), 96, 5),   # deep levels at 6x6 and 3x3: partial boxes
 ])
 def test_small_models_match_oracle(variant, ncls, filters, hw, N):
