@@ -189,7 +189,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--scene', type=int, default=SCENE)
-    ap.add_argument('--max-batch', type=int, default=63)
+    ap.add_argument('--max-batch', type=int, default=126)
     ap.add_argument('--ref-tiles', type=int, default=24)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-layers', action='store_true')
@@ -274,12 +274,13 @@ def main():
         step_device()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step_device()
-        ev1.record(stream)
-        torch.cuda.synchronize()
+    clk = ClockSampler(local_rank)
+    clk.__enter__()  # sampled over both timed legs (device-resident and end-to-end): short multi-GPU steps still get samples
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    torch.cuda.synchronize()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device='cuda')
     if world > 1:
@@ -301,6 +302,7 @@ def main():
     t_e2e = torch.tensor([(time.perf_counter() - t0) * 1e3], device='cuda')
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    clk.__exit__(None, None, None)
     e2e_ms = float(t_e2e.item()) / args.steps
     h2d = (src_row1 - src_row0) * W * BANDS * 2
     d2h = dst_rows * len(xs) * KERNEL * 5
@@ -322,6 +324,11 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        traffic = None  # DRAM bytes of the conv launches of one step: ncu-measured bytes per chip x chips of rank 0
+        tp = os.path.join(ROOT, 'profiles', 'r01_g_conv_traffic.json')
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f)['dram_bytes_per_chip'] * (r1 - r0) * len(xs)
         n_my = (r1 - r0) * len(xs)
         flops_tile = sum(times['layer_flops'])
         net_s = times['network_ms'] / 1e3
@@ -348,7 +355,8 @@ def main():
             'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all conv/convT layers of the U-Net)',
                          'achieved': tc, 'peak': pk['tc_sustained'], 'unit': 'TFLOP/s',
                          'frac': tc / pk['tc_sustained'] if pk['tc_sustained'] else None,
-                         'frac_of_burst_peak': tc / pk['tc_burst'], 'peak_burst': pk['tc_burst'], 'traffic': None,
+                         'frac_of_burst_peak': tc / pk['tc_burst'], 'peak_burst': pk['tc_burst'], 'traffic': traffic,
+                         'traffic_source': 'profiles/r01_g_conv_traffic.json (ncu dram__bytes_read+write, per chip)',
                          'peak_source': pk['source'],
                          'how': 'algorithmic FLOPs (67.41 GFLOP per 384x384x6 chip) x chips of rank 0 / CUDA-event time of '
                                 'the conv launches of the last timed step'},
