@@ -84,7 +84,8 @@ PROTOTYPES = {
 
 
 def lib_path() -> str:
-    return os.path.join(PKG, 'libscv.so')
+    # SCV_LIB_PATH: kernel-variant experiments only (tools/build_variant.sh); the product is the in-tree libscv.so
+    return os.environ.get('SCV_LIB_PATH') or os.path.join(PKG, 'libscv.so')
 
 
 def load_library():

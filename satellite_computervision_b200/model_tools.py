@@ -112,21 +112,24 @@ class UNetModel:
         self._weights_dirty = True
 
     def load_weights(self, path, by_name=False, skip_mismatch=False):
-        """``.npz`` written as ``np.savez(path, *model.get_weights())`` (arrays arr_0..arr_n).
-        Keras HDF5 files are read by :mod:`satellite_computervision_b200.keras_h5` when present."""
+        """``keras.Model.load_weights`` (``utils/model_tools.py:1162, :1200``): Keras HDF5 files (legacy
+        ``.h5`` / ``.hdf5`` full-model or weights-only, Keras 3 ``.weights.h5`` / ``.keras``) through
+        :mod:`keras_h5`, or an ``.npz`` written as ``np.savez(path, *model.get_weights())``.  Tensors are
+        taken in ``get_weights()`` order and checked for count and shape."""
         if str(path).endswith('.npz'):
             with np.load(path) as z:
                 keys = sorted(z.files, key=lambda k: int(k.split('_')[1]) if k.startswith('arr_') else 0)
                 self.set_weights([z[k] for k in keys])
             return
-        try:
-            from . import keras_h5
-        except ImportError as exc:
-            raise NotImplementedError('Keras HDF5 weight files need the keras_h5 reader; use an .npz of '
-                                      'model.get_weights()') from exc
+        from . import keras_h5
         self.set_weights(keras_h5.read_weights(path, self))
 
     def save_weights(self, path):
+        """``.npz`` of ``get_weights()``, or a legacy Keras HDF5 weights file for ``.h5`` / ``.hdf5``."""
+        if str(path).endswith(('.h5', '.hdf5')):
+            from . import keras_h5
+            keras_h5.write_weights_h5(path, keras_h5.keras_layer_groups(self))
+            return
         np.savez(path, *self._weights)
 
     def count_params(self):
