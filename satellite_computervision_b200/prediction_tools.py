@@ -182,6 +182,74 @@ def geotiff_predictions(imageDataset, model, jsonFile, kernel_buffer=[128, 128],
     return prob[..., None], proj.get('affine', {}).get('doubleMatrix'), proj.get('crs')
 
 
+# ---------------------------------------------------------------- GEE patch files in / rasters out
+class PatchDataset:
+    """What ``make_pred_dataset`` returns: an iterable of ``(1, h, w, C)`` NormalizedTensor batches
+    (``.batch(1)``, ``utils/prediction_tools.py:223-226``) that ``UNetModel.predict`` and the stitchers accept.
+    Patches are decoded lazily, file by file."""
+
+    def __init__(self, file_list, features, kernel_shape, kernel_buffer, spec_fn, one_hot, derived):
+        self.file_list, self.features = sorted(file_list), list(features)
+        self.kernel_shape, self.kernel_buffer = list(kernel_shape), list(kernel_buffer)
+        self._spec_fn, self.one_hot, self.derived = spec_fn, one_hot, derived
+
+    def __iter__(self):
+        from . import gee_io
+        for bands, extra, hot in gee_io.iter_patches(self.file_list, self.features, self.kernel_shape,
+                                                     self.kernel_buffer, self.one_hot, self.derived):
+            nb = bands.shape[-1]
+            stacked = np.concatenate([bands] + extra + hot, axis=-1) if (extra or hot) else bands
+            yield NormalizedTensor(stacked[None], self._spec_fn(nb, stacked.shape[-1]))
+
+
+def make_pred_dataset(file_list, features, kernel_shape=[256, 256], kernel_buffer=[128, 128], axes=[2], splits=None,
+                      moments=None, one_hot=None, **kwargs):
+    """``utils/prediction_tools.py:159-226``: GZIP TFRecord patch files -> per-patch HWC stack of ``features``
+    -> ``rescale_tensor(bands, axes, moments, splits)`` -> derived bands (``**kwargs`` callables) and one-hot
+    planes appended un-normalised -> batches of one.  The rescale runs inside the GPU gather kernel (the
+    dataset carries the normaliser spec); appended planes need ``moments`` so they can pass through as
+    per-band identity."""
+    from .processing import rescale_spec
+
+    def spec_fn(nbands, ntotal):
+        spec = rescale_spec(nbands, axes, 1e-8, moments, splits)
+        if ntotal == nbands:
+            return spec
+        if spec.mode != _lib.SCV_NORM_PER_BAND:
+            raise NotImplementedError('derived / one-hot bands next to a data-dependent rescale (no moments=) are '
+                                      'not implemented on the GPU path')
+        extra = ntotal - nbands
+        return NormSpec(_lib.SCV_NORM_PER_BAND, np.concatenate([spec.sub, np.zeros(extra, np.float32)]),
+                        np.concatenate([spec.div, np.ones(extra, np.float32)]), spec.eps)
+
+    return PatchDataset(list(file_list), features, kernel_shape, kernel_buffer, spec_fn, one_hot, dict(kwargs))
+
+
+def write_tfrecord_predictions(predictions, pred_path, out_image_base, kernel_shape=[256, 256], kernel_buffer=[128, 128]):
+    """``utils/prediction_tools.py:375-445``: crop every prediction and write ``{pred_path}/{out_image_base}.tfrecords``
+    (uncompressed; one Example per patch, FloatList features ``b1..bC``).  Returns the file name."""
+    import os
+    from . import gee_io
+    return gee_io.write_prediction_tfrecords(predictions, os.path.join(pred_path, f'{out_image_base}.tfrecords'),
+                                             kernel_shape, kernel_buffer)
+
+
+def write_geotiff_prediction(image, jsonFile, aoi):
+    """``utils/prediction_tools.py:447-472``: ``{aoi}.tif`` with the mixer's affine transform and CRS."""
+    from . import gee_io
+    mixer = _load_mixer(jsonFile)
+    proj = mixer.get('projection', {})
+    return gee_io.write_geotiff(f'{aoi}.tif', image, proj.get('affine', {}).get('doubleMatrix'), proj.get('crs'))
+
+
+def write_geotiff_predictions(imageDataset, model, jsonFile, outImgBase, outImgPath, kernel_buffer=[128, 128], norm=None):
+    """``utils/prediction_tools.py:475-536``: predict every patch, crop, place (channel 0, float32) and write
+    ``{outImgPath}/{outImgBase}.tif``.  Returns the file name."""
+    from . import gee_io
+    out_array, transform, crs = geotiff_predictions(imageDataset, model, jsonFile, kernel_buffer, norm=norm)
+    return gee_io.write_geotiff(gee_io.geotiff_path(outImgPath, outImgBase), out_array, transform, crs)
+
+
 def predict_overlap_chunks(chw, m, chunk=256, depth=64, norm=None):
     """Geometry T3 -- ``predict_pc_dask`` / ``run_dask`` (``utils/prediction_tools.py:818-829``,
     ``map_overlap(depth=(0,64,64), boundary=0)``) + ``predict_chunk`` (``utils/model_tools.py:1295-1300``):

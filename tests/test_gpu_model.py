@@ -150,3 +150,53 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         m.predict(np.zeros((1, 64, 64, 5), np.float32))      # wrong band count
     assert pt.predict_chips(np.zeros((96, 96, 6), np.float32), [], np.zeros((96, 96)), m, 64, 32).sum() == 0
+
+
+def test_keras_h5_weight_file_round_trip(tmp_path):
+    """save_weights('.h5') -> a fresh model's load_weights: same predictions bit for bit (N1)."""
+    m, w = _mk('A', 6, 1, (32, 64), seed=7)
+    x = np.random.default_rng(5).random((2, 64, 64, 6)).astype(np.float32)
+    want = m.predict(x)
+    for name in ('weights.hdf5', 'weights.npz'):
+        path = str(tmp_path / name)
+        m.save_weights(path)
+        m2 = model_tools.binary_unet(nchannels=6, filters=[32, 64])
+        assert not np.array_equal(m2.predict(x), want)
+        m2.load_weights(path)
+        assert np.array_equal(m2.predict(x), want)
+    m3 = model_tools.binary_unet(nchannels=6, filters=[32, 64, 128])
+    with pytest.raises(ValueError):
+        m3.load_weights(str(tmp_path / 'weights.hdf5'))     # wrong architecture: count / shape mismatch
+
+
+def test_gee_patch_files_to_geotiff(tmp_path):
+    """GEE workflow end to end (N2, N3): .tfrecord.gz patches + mixer.json -> make_pred_dataset ->
+    write_geotiff_predictions == the array path; prediction TFRecords hold the cropped patches."""
+    import json
+    from PIL import Image
+    from satellite_computervision_b200 import gee_io
+    m, w = _mk('A', 6, 1, (32, 64), seed=8)
+    rng = np.random.default_rng(6)
+    cols, rows, k, b = 3, 2, 64, 32
+    feats = ['B2', 'B3', 'B4', 'B8', 'B11', 'B12']
+    patches = (rng.random((cols * rows, k + b, k + b, 6)) * 3000).astype(np.float32)
+    gee_io.write_patch_tfrecords(str(tmp_path / 'img00000.tfrecord.gz'), patches[:4], feats)
+    gee_io.write_patch_tfrecords(str(tmp_path / 'img00001.tfrecord.gz'), patches[4:], feats)
+    mixer = {'projection': {'crs': 'EPSG:32618', 'affine': {'doubleMatrix': [10.0, 0.0, 5e5, 0.0, -10.0, 4.2e6]}},
+             'patchDimensions': [k, k], 'patchesPerRow': cols, 'totalPatches': cols * rows}
+    jf = str(tmp_path / 'img-mixer.json')
+    with open(jf, 'w') as f:
+        json.dump(mixer, f)
+    mm = [(0.0, 3000.0)] * 6
+    files = [str(tmp_path / f'img0000{i}.tfrecord.gz') for i in (1, 0)]
+    ds = pt.make_pred_dataset(files, feats, [k, k], [b, b], moments=mm)
+    tif = pt.write_geotiff_predictions(ds, m, jf, 'pred', str(tmp_path), [b, b])
+    want, _, _ = pt.geotiff_predictions(processing.rescale_tensor(patches, moments=mm), m, mixer, [b, b])
+    with Image.open(tif) as im:
+        assert np.array_equal(np.array(im), want[..., 0])
+    preds = m.predict(pt.make_pred_dataset(files, feats, [k, k], [b, b], moments=mm), steps=cols * rows)
+    out = pt.write_tfrecord_predictions(preds, str(tmp_path), 'pred', [k, k], [b, b])
+    recs = [gee_io.parse_example(r) for r in gee_io.read_tfrecords(out, verify=True)]
+    assert len(recs) == cols * rows
+    stitched = np.block([[recs[r * cols + c]['b1'].reshape(k, k) for c in range(cols)] for r in range(rows)])
+    assert np.array_equal(stitched, want[..., 0])
