@@ -181,6 +181,31 @@ def test_extract_per_band_bit_exact(dtype):
         assert np.all(got[i, :, :, Cc:] == 0)
 
 
+def test_extract_u16_fast_path_bit_exact(monkeypatch):
+    """uint16 x 6 bands x per-band constants runs a dedicated kernel (with and without a subtract): the same
+    bits as the generic kernel and as bf16(reference normaliser), including every value that lands within a
+    few fp32 ulps of a bf16 rounding boundary (all 65536 digital numbers are present)."""
+    rng = np.random.default_rng(9)
+    H, W = 160, 431
+    arr = rng.integers(0, 65536, (H, W, 6), dtype=np.uint16)
+    arr.reshape(-1)[:65536 * 6] = np.repeat(np.arange(65536, dtype=np.uint16), 6)  # every DN in every band
+    kernel, buff = 64, 32
+    idx = otile.generate_chip_indices(arr.shape, buff, kernel)
+    for spec, mm in ((processing.scalar_spec(6, 10000.0), None),
+                     (processing.rescale_spec(6, moments=[(0, 10000), (3.0, 9000.5), (0.0, 8000.5), (1.0, 3000.0), (0.0, 65535.0), (200.0, 7000.0)]),
+                      [(0, 10000), (3.0, 9000.5), (0.0, 8000.5), (1.0, 3000.0), (0.0, 65535.0), (200.0, 7000.0)])):
+        got = _extract(arr, (kernel, buff), spec, idx)
+        monkeypatch.setenv('SCV_K1_GENERIC', '1')
+        generic = _extract(arr, (kernel, buff), spec, idx)
+        monkeypatch.delenv('SCV_K1_GENERIC')
+        assert np.array_equal(got, generic)
+        for i, (y, x) in enumerate(idx):
+            chip = arr[y - 16:y + 80, x - 16:x + 80, :].astype(np.float32)
+            want = onorm.rescale_tensor(chip, moments=mm) if mm else chip / np.float32(10000.0)
+            assert np.array_equal(got[i, :, :, :6], G.bf16_round(want)), i
+            assert np.all(got[i, :, :, 6:] == 0)
+
+
 def test_extract_pixel_and_tile_modes():
     rng = np.random.default_rng(4)
     arr = (rng.random((200, 216, 6)) * 5000 + 100).astype(np.float32)
