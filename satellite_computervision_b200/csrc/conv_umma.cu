@@ -5,7 +5,10 @@ namespace scv {
 
 namespace {
 template <int KC, int BN, int EPI>
+cudaError_t launch_ptile(const ConvLaunch& L, cudaStream_t stream);
+template <int KC, int BN, int EPI>
 cudaError_t launch_one(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.slab == 3) return launch_ptile<KC, BN, EPI>(L, stream);
   if (L.slab) {
     constexpr int NTAPS = EPI == EPI_CONVT ? 1 : 9;
     if (L.p.ntaps != NTAPS) return cudaErrorInvalidValue;
@@ -25,9 +28,16 @@ cudaError_t launch_one(const ConvLaunch& L, cudaStream_t stream) {
   return cudaGetLastError();
 }
 template <int KC, int BN, int EPI>
+cudaError_t launch_ptile(const ConvLaunch& L, cudaStream_t stream) {
+  conv_ptile_kernel<KC, BN, EPI><<<L.grid, kPtileThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  return cudaGetLastError();
+}
+template <int KC, int BN, int EPI>
 cudaError_t attr_one() {
   const int kMax = 227 * 1024;
   cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_ptile_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
   if (e != cudaSuccess) return e;
   constexpr int NTAPS = EPI == EPI_CONVT ? 1 : 9;
   e = cudaFuncSetAttribute(conv_slab_kernel<KC, BN, EPI, NTAPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);

@@ -483,6 +483,202 @@ __global__ void __launch_bounds__(kConvThreads)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent form of conv_umma_kernel for the deep / mid layers (weights too large to keep resident, K long):
+// one CTA per SM walks the (M tile, N tile) work list with the SAME per-tile K order, so results are
+// bit-identical to the one-tile-per-CTA kernel.  What it removes is the per-CTA fixed cost that kernel pays
+// for every 128 x BN tile -- TMEM allocation, barrier init, a cold TMA pipeline, and an epilogue the tensor
+// pipe waits for: here the TMA ring keeps running across tile boundaries and two TMEM accumulators
+// (2 x BN <= 512 columns) alternate, so epilogue warpgroup g drains tile j while the issuer runs tile j+1.
+constexpr int kPtileThreads = 64 + 256;  // warp 0: TMA, warp 1: MMA + TMEM alloc, 2 epilogue warpgroups
+// floats of epilogue constants per warpgroup (bias + skip (s,t) / head (w,b)), 16-byte multiple
+__host__ __device__ inline int kPtileConstStride(int BN, int epi, int ncls) {
+  int n = BN;
+  if (epi == EPI_POOL_SKIP) n += 2 * BN;
+  if (epi == EPI_HEAD) n += BN * ncls + ncls;
+  return (n + 3) & ~3;
+}
+__host__ __device__ inline size_t ptile_smem_bytes(int KC, int BN, int nstage, int epi, int ncls) {
+  size_t s = 1024 + static_cast<size_t>(nstage) * conv_stage_bytes(KC, BN);
+  s += (2 * nstage + 4) * 8 + 16;
+  s += 2 * static_cast<size_t>(kPtileConstStride(BN, epi, ncls)) * 4;
+  return s + 64;
+}
+
+template <int KC, int BN, int EPI>
+__global__ void __launch_bounds__(kPtileThreads, 1)
+    conv_ptile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const ConvParams p) {
+  constexpr int A_BYTES = 128 * KC * 2;
+  constexpr int B_BYTES = BN * KC * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ROW_BYTES = KC * 2;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
+  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nstage = p.nstage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + static_cast<size_t>(nstage) * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + nstage;
+  uint64_t* acc_full = empty_bar + nstage;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks = p.Cin / KC;
+  const int iters = p.ntaps * chunks;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < nstage; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&acc_full[a], 1);
+        mbar_init(&acc_empty[a], 128);
+      }
+      *abort_flag = 0;
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one uninterrupted stage stream over all tiles of this CTA ==========
+    uint32_t s = 0, ph = 1;
+    bool run = true;
+    for (int w = blockIdx.x; run && w < total; w += gridDim.x) {
+      const int n_tile = w % p.n_tiles_n;
+      int m_tile = w / p.n_tiles_n;
+      const int tx = m_tile % p.tiles_x;
+      m_tile /= p.tiles_x;
+      const int ty = m_tile % p.tiles_y;
+      const int tn = m_tile / p.tiles_y;
+      const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.TN, nb0 = n_tile * BN;
+      int ch = 0, tap = 0;
+      for (int it = 0; it < iters; ++it) {
+        const bool ok = mbar_wait(&empty_bar[s], ph, abort_flag, p.watchdog_ns);
+        if (!__all_sync(0xffffffffu, ok)) {
+          run = false;
+          break;
+        }
+        int dy = 0, dx = 0;
+        if (p.ntaps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        uint8_t* a_dst = tiles + static_cast<size_t>(s) * STAGE_BYTES;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_4d(a_dst, &tmA, &full_bar[s], ch * KC, x0 + dx, y0 + dy, n0 + p.n_in_off);
+          tma_load_2d(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + ch * KC, nb0);
+        }
+        __syncwarp();
+        if (++tap == p.ntaps) {
+          tap = 0;
+          ++ch;
+        }
+        if (++s == static_cast<uint32_t>(nstage)) s = 0, ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t s = 0, ph = 0, j = 0;
+    bool run = true;
+    for (int w = blockIdx.x; run && w < total; w += gridDim.x, ++j) {
+      const uint32_t a = j & 1;
+      const bool ok0 = mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1, abort_flag, p.watchdog_ns);
+      if (!__all_sync(0xffffffffu, ok0)) break;
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + a * BN;
+      for (int it = 0; it < iters; ++it) {
+        const bool ok = mbar_wait(&full_bar[s], ph, abort_flag, p.watchdog_ns);
+        if (!__all_sync(0xffffffffu, ok)) {
+          run = false;
+          break;
+        }
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * STAGE_BYTES);
+        const uint64_t da0 = umma_smem_desc(a_addr, ROW_BYTES);
+        const uint64_t db0 = umma_smem_desc(a_addr + A_BYTES, ROW_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            umma_bf16(tacc, da0 + 2 * k, db0 + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+        if (++s == static_cast<uint32_t>(nstage)) s = 0, ph ^= 1;
+      }
+      if (run && elect_one()) umma_commit(&acc_full[a]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: warpgroup g drains this CTA's tiles g, g+2, ... =====================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int xx = r % p.TW;
+    const int yy = (r / p.TW) % p.TH;
+    const int nn = r / (p.TW * p.TH);
+    // each warpgroup keeps its own copy of the epilogue constants (the two groups may be on different N tiles)
+    uint32_t j = g;
+    int last_n_tile = -1;
+    for (int w = blockIdx.x + g * gridDim.x; w < total; w += 2 * gridDim.x, j += 2) {
+      const int n_tile = w % p.n_tiles_n;
+      int m_tile = w / p.n_tiles_n;
+      const int tx = m_tile % p.tiles_x;
+      m_tile /= p.tiles_x;
+      const int ty = m_tile % p.tiles_y;
+      const int tn = m_tile / p.tiles_y;
+      const int x = tx * p.TW + xx, y = ty * p.TH + yy, n = tn * p.TN + nn;
+      const int nb0 = n_tile * BN;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+      float* c_bias = s_bias + g * kPtileConstStride(BN, EPI, p.ncls);
+      float* c_extra = c_bias + BN;
+      if (n_tile != last_n_tile) {  // this group's constants: named barrier over the group's 128 threads
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        load_epilogue_consts<BN, EPI>(p, (warp - 2 - 4 * g) * 32 + lane, 128, nb0, c_bias, c_extra);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        last_n_tile = n_tile;
+      }
+      const bool ready = mbar_wait(&acc_full[g], (j >> 1) & 1, abort_flag, p.watchdog_ns);
+      if (!__all_sync(0xffffffffu, ready)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if constexpr (EPI == EPI_HEAD)
+        epilogue_head<BN>(p, taddr, xx, yy, x, y, n, valid, nb0, c_bias, c_extra);
+      else
+        epilogue_tile<BN, EPI>(p, taddr, xx, yy, x, y, n, valid, p.TW, nb0, c_bias, c_extra);
+      tc_fence_before();
+      mbar_arrive(&acc_empty[g]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tmem_dealloc(tmem_base, 2 * BN);
+    if (lane == 0 && *abort_flag) atomicExch(p.err, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Persistent, weight-stationary variant for the high-resolution layers (small Cin*Cout, huge M).
 //
 // The tile kernel above re-fetches the A tile once per tap (9x L2->smem traffic) and spends a CTA
@@ -753,7 +949,7 @@ struct ConvLaunch {
   CUtensorMap tmOut, tmPool;  // slab kernel only: TMA-store maps of the bf16 outputs
   ConvParams p;
   int KC, BN, EPI;
-  int slab;  // 2: conv_rows_kernel (row streaming, conv_rows.cuh), 1: conv_slab_kernel (persistent), 0: conv_umma_kernel
+  int slab;  // 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
   int nacc;  // slab kernel: accumulators / epilogue warpgroups (2 or 4)
   int grid;
   size_t smem;

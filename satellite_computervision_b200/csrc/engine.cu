@@ -755,6 +755,19 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   L->grid = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_n;
   L->tmB = l.tmB;
   L->smem = conv_smem_bytes(l.KC, l.BN, p.nstage, l.epi, e ? e->arch.cfg.nclasses : 1);
+  // enough tiles for every SM to loop: persistent form (same K order per tile -> same bits)
+  const int ncls = e ? e->arch.cfg.nclasses : 1;
+  const int sms = sm_count() / p.n_tiles_n * p.n_tiles_n;
+  if (env_int("SCV_PTILE", 1) && sms > 0 && (L->grid >= 2 * sms || env_int("SCV_PTILE", 1) == 2)) {
+    int ns = 8;
+    while (ns > 2 && ptile_smem_bytes(l.KC, l.BN, ns, l.epi, ncls) > kSlabSmemBudget) --ns;
+    if (!(e && e->opt_stages > 0)) p.nstage = std::min(ns, std::max(2, iters * 2));
+    else p.nstage = std::max(2, std::min(ns, e->opt_stages));
+    p.ncls = ncls;
+    L->slab = 3;
+    L->grid = std::min(L->grid, sms);
+    L->smem = ptile_smem_bytes(l.KC, l.BN, p.nstage, l.epi, ncls);
+  }
   SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, p.TW, p.TH, p.TN));
   return SCV_OK;
 }
@@ -838,8 +851,9 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
       fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,
-              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile"), Ln.KC, Ln.BN,
-              Ln.slab ? "nslab" : "nstage", Ln.slab ? Ln.p.nslab : Ln.p.nstage, Ln.slab ? Ln.nacc : 1, Ln.grid, Ln.smem);
+              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 3 ? "ptile" : (Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile")), Ln.KC, Ln.BN,
+              (Ln.slab == 1 || Ln.slab == 2) ? "nslab" : "nstage", (Ln.slab == 1 || Ln.slab == 2) ? Ln.p.nslab : Ln.p.nstage,
+              Ln.slab == 3 ? 2 : (Ln.slab ? Ln.nacc : 1), Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
   *out = pl.get();

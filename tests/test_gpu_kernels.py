@@ -105,6 +105,49 @@ def test_conv3x3_matches_torch(N, H, W, Cin, Cout):
     assert s['nan'] == 0 and s['n_bad'] == 0, s
 
 
+@pytest.mark.parametrize('N,H,W,Cin,Cout,grid', [
+    (1, 16, 16, 128, 256, 1),     # one CTA walks all tiles, 2 channel chunks
+    (1, 8, 16, 256, 512, 2),      # 2 N tiles: each CTA keeps its N tile
+    (5, 12, 12, 128, 256, 3),     # box 4x4x8, image tail, odd tile count over 3 CTAs
+    (3, 24, 24, 64, 64, 2),       # box 8x8x2
+    (2, 20, 20, 32, 128, 4),      # partial tiles (masked stores), KC=32
+    (1, 16, 48, 3, 64, 1),        # KC=16
+])
+def test_persistent_tile_kernel_equals_tile_kernel(N, H, W, Cin, Cout, grid, monkeypatch):
+    """conv_ptile_kernel (persistent, two TMEM accumulators) against torch and, bit for bit, against the
+    one-tile-per-CTA kernel it replaces for large launches."""
+    rng = np.random.default_rng(31 + N + H + Cin)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    monkeypatch.setenv('SCV_ROWS', '0')
+    monkeypatch.setenv('SCV_SLAB', '0')
+    monkeypatch.setenv('SCV_PTILE', '0')
+    ref_kernel = G.conv3x3_device(x, k, b)
+    monkeypatch.setenv('SCV_PTILE', '2')
+    monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
+    got = G.conv3x3_device(x, k, b)
+    s = G.err_stats(got, G.conv3x3_ref(x, k, b))
+    assert s['nan'] == 0 and s['n_bad'] == 0, s
+    assert np.array_equal(got, ref_kernel)
+    if H % 2 == 0 and W % 2 == 0:
+        y, p = G.conv3x3_device(x, k, b, pooled=True)
+        assert np.array_equal(y, ref_kernel) and np.array_equal(p, G.maxpool_ref(y))
+
+
+def test_persistent_tile_kernel_convT(monkeypatch):
+    rng = np.random.default_rng(41)
+    x = rng.standard_normal((2, 6, 6, 1024)).astype(np.float32)
+    k = (rng.standard_normal((2, 2, 512, 1024)) / 32).astype(np.float32)
+    b = rng.standard_normal(512).astype(np.float32) * 0.1
+    monkeypatch.setenv('SCV_PTILE', '0')
+    ref_kernel = G.convT_device(x, k, b)
+    monkeypatch.setenv('SCV_PTILE', '2')
+    monkeypatch.setenv('SCV_DEBUG_GRID', '8')
+    got = G.convT_device(x, k, b)
+    assert G.err_stats(got, G.convT_ref(x, k, b))['n_bad'] == 0 and np.array_equal(got, ref_kernel)
+
+
 def test_conv3x3_without_relu_keeps_negatives():
     rng = np.random.default_rng(5)
     x = rng.standard_normal((1, 16, 16, 32)).astype(np.float32)
