@@ -1,4 +1,5 @@
 // Instantiations + dispatch of the UMMA implicit-GEMM convolution kernels.
+#include "conv_slabw.cuh"
 #include "conv_umma.cuh"
 
 namespace scv {
@@ -130,6 +131,7 @@ cudaError_t attr_kc8() {
 
 cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   if (L.slab == 2) return conv_rows_launch(L, stream);
+  if (L.slab == 4) return conv_slabw_launch(L, stream);
   if (L.KC == 8) {
     switch (L.BN) {
       case 32: return launch_kc8<32>(L, stream);
@@ -157,6 +159,7 @@ cudaError_t conv_init_attributes() {
   if ((e = attr_bn<32>()) != cudaSuccess) return e;
   if ((e = attr_bn<64>()) != cudaSuccess) return e;
   if ((e = conv_rows_init_attributes()) != cudaSuccess) return e;
+  if ((e = conv_slabw_init_attributes()) != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
 }

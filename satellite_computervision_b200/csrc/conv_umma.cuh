@@ -489,7 +489,12 @@ __global__ void __launch_bounds__(kConvThreads)
 // for every 128 x BN tile -- TMEM allocation, barrier init, a cold TMA pipeline, and an epilogue the tensor
 // pipe waits for: here the TMA ring keeps running across tile boundaries and two TMEM accumulators
 // (2 x BN <= 512 columns) alternate, so epilogue warpgroup g drains tile j while the issuer runs tile j+1.
-constexpr int kPtileThreads = 64 + 256;  // warp 0: TMA, warp 1: MMA + TMEM alloc, 2 epilogue warpgroups
+// warp 0: TMA; warps 1..kPtileIssuers: MMA issuers taking turns stage by stage (an issuer's barrier waits,
+// descriptor arithmetic and tcgen05.commit run while the others issue; the token keeps issue order -- and with
+// it the summation order -- strictly sequential, as in conv_rows_kernel); then 2 epilogue warpgroups.
+constexpr int kPtileIssuers = 2;
+constexpr int kPtileFirstEpiWarp = 1 + kPtileIssuers;
+constexpr int kPtileThreads = 32 * kPtileFirstEpiWarp + 256;
 // floats of epilogue constants per warpgroup (bias + skip (s,t) / head (w,b)), 16-byte multiple
 __host__ __device__ inline int kPtileConstStride(int BN, int epi, int ncls) {
   int n = BN;
@@ -499,7 +504,7 @@ __host__ __device__ inline int kPtileConstStride(int BN, int epi, int ncls) {
 }
 __host__ __device__ inline size_t ptile_smem_bytes(int KC, int BN, int nstage, int epi, int ncls) {
   size_t s = 1024 + static_cast<size_t>(nstage) * conv_stage_bytes(KC, BN);
-  s += (2 * nstage + 4) * 8 + 16;
+  s += (2 * nstage + 4 + kPtileIssuers) * 8 + 16;
   s += 2 * static_cast<size_t>(kPtileConstStride(BN, epi, ncls)) * 4;
   return s + 64;
 }
@@ -522,7 +527,8 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
   uint64_t* empty_bar = full_bar + nstage;
   uint64_t* acc_full = empty_bar + nstage;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* turn = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + kPtileIssuers);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
@@ -546,6 +552,7 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
         mbar_init(&acc_full[a], 1);
         mbar_init(&acc_empty[a], 128);
       }
+      for (int i = 0; i < kPtileIssuers; ++i) mbar_init(&turn[i], 1);
       *abort_flag = 0;
       fence_barrier_init();
     }
@@ -596,41 +603,62 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
         if (++s == static_cast<uint32_t>(nstage)) s = 0, ph ^= 1;
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    uint32_t s = 0, ph = 0, j = 0;
-    bool run = true;
+  } else if (warp < kPtileFirstEpiWarp) {
+    // ===================== MMA issuers: issuer k takes the CTA's stages k, k+ni, ... =====================
+    const int ni = p.n_issuers;  // <= min(kPtileIssuers, nstage, 2 * iters): reuse distances cover the issuers in flight
+    const int me = warp - 1;
+    uint32_t s = 0, ph = 0, j = 0, nth = 0;
+    int turn_of = 0;
+    bool run = me < ni;
     for (int w = blockIdx.x; run && w < total; w += gridDim.x, ++j) {
       const uint32_t a = j & 1;
-      const bool ok0 = mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1, abort_flag, p.watchdog_ns);
-      if (!__all_sync(0xffffffffu, ok0)) break;
-      tc_fence_after();
       const uint32_t tacc = tmem_base + a * BN;
-      for (int it = 0; it < iters; ++it) {
-        const bool ok = mbar_wait(&full_bar[s], ph, abort_flag, p.watchdog_ns);
+      for (int it = 0; it < iters; ++it, ++turn_of) {
+        if (turn_of == ni) turn_of = 0;
+        const uint32_t sc = s, phc = ph;
+        if (++s == static_cast<uint32_t>(nstage)) s = 0, ph ^= 1;
+        if (turn_of != me) continue;
+        // ---- everything that does not need the token
+        if (it == 0) {  // first stage of a tile: its accumulator must have been drained
+          const bool ok0 = mbar_wait(&acc_empty[a], ((j >> 1) & 1) ^ 1, abort_flag, p.watchdog_ns);
+          if (!__all_sync(0xffffffffu, ok0)) {
+            run = false;
+            break;
+          }
+        }
+        const bool ok = mbar_wait(&full_bar[sc], phc, abort_flag, p.watchdog_ns);
         if (!__all_sync(0xffffffffu, ok)) {
           run = false;
           break;
         }
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(s) * STAGE_BYTES);
+        const uint32_t a_addr = smem_u32(tiles + static_cast<size_t>(sc) * STAGE_BYTES);
         const uint64_t da0 = umma_smem_desc(a_addr, ROW_BYTES);
         const uint64_t db0 = umma_smem_desc(a_addr + A_BYTES, ROW_BYTES);
+        // ---- the turn: stage g may only be issued after stage g-1
+        if (ni > 1) {
+          const uint32_t par = me == 0 ? ((nth & 1) ^ 1) : (nth & 1);
+          const bool ok3 = mbar_wait(&turn[me], par, abort_flag, p.watchdog_ns);
+          if (!__all_sync(0xffffffffu, ok3)) {
+            run = false;
+            break;
+          }
+        }
+        tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k)
+          for (int k = 0; k < KC / 16; ++k)  // +32 B per k step == +2 in the descriptor's 16-byte address units
             umma_bf16(tacc, da0 + 2 * k, db0 + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          if (ni > 1) mbar_arrive(&turn[me + 1 == ni ? 0 : me + 1]);  // hand the token on before the commits
+          umma_commit(&empty_bar[sc]);                                 // frees this smem stage once its MMAs retire
+          if (it == iters - 1) umma_commit(&acc_full[a]);              // in-order pipe: the tile's last MMA retires last
         }
         __syncwarp();
-        if (++s == static_cast<uint32_t>(nstage)) s = 0, ph ^= 1;
+        ++nth;
       }
-      if (run && elect_one()) umma_commit(&acc_full[a]);
-      __syncwarp();
     }
   } else {
     // ===================== epilogue: warpgroup g drains this CTA's tiles g, g+2, ... =====================
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - kPtileFirstEpiWarp) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int xx = r % p.TW;
@@ -653,7 +681,7 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
       float* c_extra = c_bias + BN;
       if (n_tile != last_n_tile) {  // this group's constants: named barrier over the group's 128 threads
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-        load_epilogue_consts<BN, EPI>(p, (warp - 2 - 4 * g) * 32 + lane, 128, nb0, c_bias, c_extra);
+        load_epilogue_consts<BN, EPI>(p, (warp - kPtileFirstEpiWarp - 4 * g) * 32 + lane, 128, nb0, c_bias, c_extra);
         asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         last_n_tile = n_tile;
       }
@@ -949,7 +977,7 @@ struct ConvLaunch {
   CUtensorMap tmOut, tmPool;  // slab kernel only: TMA-store maps of the bf16 outputs
   ConvParams p;
   int KC, BN, EPI;
-  int slab;  // 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
+  int slab;  // 4: conv_slabw_kernel (conv_slabw.cuh), 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
   int nacc;  // slab kernel: accumulators / epilogue warpgroups (2 or 4)
   int grid;
   size_t smem;

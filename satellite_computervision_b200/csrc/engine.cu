@@ -18,6 +18,7 @@
 
 #include "../../include/scv.h"
 #include "conv_rows.cuh"
+#include "conv_slabw.cuh"
 #include "conv_umma.cuh"
 #include "tile_kernels.cuh"
 
@@ -719,6 +720,31 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, kRowsSlabPx, 2, 1));
     return SCV_OK;
   }
+  // weight-streaming halo-slab kernel: Cout = 128 layers whose 3x3 weights exceed shared memory (conv_slabw.cuh);
+  // same summation order as the slab / tile kernels, so the choice may depend on the batch size
+  if (env_int("SCV_SLABW", 1) && l.kind == L_CONV3 && l.KC == 64 && l.ntotal == 128 &&
+      l.cin_pad >= env_int("SCV_SLABW_MIN_CIN", 64) && (l.epi == EPI_STORE || l.epi == EPI_POOL_SKIP) && w % 8 == 0 && h % 16 == 0 &&
+      ((long long)B * (h / 16) * (w / 8) >= 4LL * sm_count() || env_int("SCV_SLABW", 1) == 2)) {
+    int nbr = 6;
+    while (nbr > 2 && slabw_smem_bytes(64, 128, nbr, l.epi) > kSlabSmemBudget) --nbr;
+    L->slab = 4;
+    L->BN = 128;
+    L->nacc = 4;
+    p.TW = 8, p.TH = 16, p.TN = 1;
+    p.tiles_x = w / 8;
+    p.tiles_y = h / 16;
+    p.tiles_n = B;
+    p.num_m_tiles = p.tiles_x * p.tiles_y * B;
+    p.n_tiles_n = 1;
+    p.nstage = nbr;
+    p.n_issuers = std::max(1, std::min(kSlabwIssuers, env_int("SCV_SLABW_ISSUERS", kSlabwIssuers)));
+    L->grid = (int)std::min<long long>(sm_count(), p.num_m_tiles);
+    L->smem = slabw_smem_bytes(64, 128, nbr, l.epi);
+    if (l.BN != 128) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, 128));
+    else L->tmB = l.tmB;
+    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, 10, 18, 1));
+    return SCV_OK;
+  }
   if (plan_slab(l, B, h, w, &bn, &ns, &nacc)) {
     L->nacc = nacc;
     const int sw = p.ntaps == 9 ? 10 : 8, sh = p.ntaps == 9 ? 18 : 16;
@@ -764,6 +790,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     if (!(e && e->opt_stages > 0)) p.nstage = std::min(ns, std::max(2, iters * 2));
     else p.nstage = std::max(2, std::min(ns, e->opt_stages));
     p.ncls = ncls;
+    p.n_issuers = std::max(1, std::min({kPtileIssuers, p.nstage, 2 * iters, env_int("SCV_PTILE_ISSUERS", kPtileIssuers)}));
     L->slab = 3;
     L->grid = std::min(L->grid, sms);
     L->smem = ptile_smem_bytes(l.KC, l.BN, p.nstage, l.epi, ncls);
@@ -774,7 +801,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
 
 // TMA-store maps of a slab launch's bf16 outputs (call once the output pointers are known).
 static int finish_slab_maps(ConvLaunch* L, const LayerDef& l) {
-  if (!L->slab || l.epi == EPI_HEAD) return SCV_OK;
+  if (!L->slab || L->slab == 3 || l.epi == EPI_HEAD) return SCV_OK;
   const ConvParams& p = L->p;
   const int cb = 32;  // kStageRowB / 2 channels per store box
   if (L->slab == 2) {  // row kernel: one warp stores 32 pixels of two rows
@@ -851,7 +878,7 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
       fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,
-              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 3 ? "ptile" : (Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile")), Ln.KC, Ln.BN,
+              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 4 ? "slabw" : (Ln.slab == 3 ? "ptile" : (Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile"))), Ln.KC, Ln.BN,
               (Ln.slab == 1 || Ln.slab == 2) ? "nslab" : "nstage", (Ln.slab == 1 || Ln.slab == 2) ? Ln.p.nslab : Ln.p.nstage,
               Ln.slab == 3 ? 2 : (Ln.slab ? Ln.nacc : 1), Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);

@@ -135,6 +135,34 @@ def test_persistent_tile_kernel_equals_tile_kernel(N, H, W, Cin, Cout, grid, mon
         assert np.array_equal(y, ref_kernel) and np.array_equal(p, G.maxpool_ref(y))
 
 
+@pytest.mark.parametrize('N,H,W,Cin,Cout,grid', [
+    (2, 32, 32, 128, 128, 0),     # 2 chunks, 16 tiles over 16 CTAs (single-tile passes)
+    (1, 48, 96, 256, 128, 3),     # 4 chunks, 36 tiles over 3 CTAs: 6 two-tile passes each, rings wrap
+    (3, 16, 24, 128, 128, 2),     # 9 tiles over 2 CTAs: odd tile counts -> a one-tile tail pass
+    (1, 32, 16, 64, 128, 1),      # one chunk
+])
+def test_weight_streaming_slab_kernel(N, H, W, Cin, Cout, grid, monkeypatch):
+    """conv_slabw_kernel (halo slabs + streamed weights shared by two M tiles) against torch and, bit for bit,
+    against the one-tile-per-CTA kernel (same (chunk, tap, k) summation order); pooled epilogue too."""
+    rng = np.random.default_rng(51 + N + H + Cin)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    for name in ('SCV_ROWS', 'SCV_SLAB', 'SCV_PTILE', 'SCV_SLABW'):
+        monkeypatch.setenv(name, '0')
+    ref_kernel = G.conv3x3_device(x, k, b)
+    monkeypatch.setenv('SCV_SLABW', '2')
+    monkeypatch.setenv('SCV_SLABW_MIN_CIN', '64')
+    if grid:
+        monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
+    got = G.conv3x3_device(x, k, b)
+    s = G.err_stats(got, G.conv3x3_ref(x, k, b))
+    assert s['nan'] == 0 and s['n_bad'] == 0, s
+    assert np.array_equal(got, ref_kernel)
+    y, p = G.conv3x3_device(x, k, b, pooled=True)
+    assert np.array_equal(y, ref_kernel) and np.array_equal(p, G.maxpool_ref(y))
+
+
 def test_persistent_tile_kernel_convT(monkeypatch):
     rng = np.random.default_rng(41)
     x = rng.standard_normal((2, 6, 6, 1024)).astype(np.float32)
