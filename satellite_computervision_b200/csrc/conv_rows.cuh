@@ -142,21 +142,31 @@ __device__ __forceinline__ RowsPiece rows_piece(uint32_t tmem_base, int j, int n
   return r;
 }
 
-// The 3 * KC/16 UMMAs of one input row and one channel chunk (issued by one elected thread).
+// The 3 * KC/16 UMMAs of one input row and one channel chunk (issued by one elected thread).  Descriptors are
+// handled as 32-bit low words (14-bit address field + constants) with one shared high word.
 template <int KC, int COUT>
-__device__ __forceinline__ void rows_issue_row(uint64_t da0, uint64_t db0, uint32_t d1, uint32_t id1, uint32_t d2,
-                                               uint32_t id2, uint32_t b_off, uint32_t b_wrap) {
+__device__ __forceinline__ void rows_issue_row(uint32_t da0, uint32_t db0, uint32_t desc_hi, uint32_t d1, uint32_t id1,
+                                               uint32_t d2, uint32_t id2, uint32_t b_off, uint32_t b_wrap) {
   constexpr int ROWB = KC * 2, WT_BLOCK = COUT * ROWB;
-  const uint64_t dbr = db0 + b_off * (WT_BLOCK >> 4);
-  const uint64_t wrap = b_wrap * (WT_BLOCK >> 4);
+  const uint32_t dbr = db0 + b_off * (WT_BLOCK >> 4);
+  if (id2 == 0) {  // common case: one piece
 #pragma unroll
-  for (int kx = 0; kx < 3; ++kx) {
+    for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-    for (int k = 0; k < KC / 16; ++k) {
-      const uint64_t da = da0 + static_cast<uint64_t>((kx * ROWB + k * 32) >> 4);
-      const uint64_t db = dbr + static_cast<uint64_t>((kx * 3 * WT_BLOCK + k * 32) >> 4);
-      umma_bf16(d1, da, db, id1, 1u);
-      if (id2) umma_bf16(d2, da, db + wrap, id2, 1u);
+      for (int k = 0; k < KC / 16; ++k)
+        umma_bf16_lo(d1, da0 + ((kx * ROWB + k * 32) >> 4), dbr + ((kx * 3 * WT_BLOCK + k * 32) >> 4), desc_hi, id1);
+    }
+  } else {         // the row accumulators wrap around the TMEM ring: two pieces per (kx, k)
+    const uint32_t wrap = b_wrap * (WT_BLOCK >> 4);
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int k = 0; k < KC / 16; ++k) {
+        const uint32_t da = da0 + ((kx * ROWB + k * 32) >> 4);
+        const uint32_t db = dbr + ((kx * 3 * WT_BLOCK + k * 32) >> 4);
+        umma_bf16_lo(d1, da, db, desc_hi, id1);
+        umma_bf16_lo(d2, da, db + wrap, desc_hi, id2);
+      }
     }
   }
 }
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     bool run = me < ni && __all_sync(0xffffffffu, mbar_wait(w_full, 0, abort_flag, p.watchdog_ns));
     tc_fence_after();
     const uint32_t w_desc = static_cast<uint32_t>(umma_smem_desc(smem_u32(w_smem), ROWB) & 0xffffffffu);
-    const uint64_t desc_hi = umma_smem_desc(0, ROWB) & 0xffffffff00000000ull;
+    const uint32_t desc_hi = static_cast<uint32_t>(umma_smem_desc(0, ROWB) >> 32);
     const uint32_t slab0_desc = static_cast<uint32_t>(umma_smem_desc(smem_u32(slabs), ROWB) & 0xffffffffu);
     uint32_t nth = 0;    // pairs this issuer has issued
     int turn_of = 0;     // t % ni without the division
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     uint32_t s0 = static_cast<uint32_t>(me * chunks) % nslab, ph0 = (static_cast<uint32_t>(me * chunks) / nslab) & 1;
     uint32_t t = 0;      // running input-pair counter of this CTA (all issuers count all pairs)
     uint32_t opc = 0;    // running output-pair counter at the start of the current segment
-    long long t_wait = 0, t_turn = 0, t_issue = 0, t_begin = ROWS_CLOCK();
+    long long t_wait = 0, t_turn = 0, t_issue = 0, t_mma = 0, t_hand = 0, t_begin = ROWS_CLOCK();
     long long pc = p0;
     RowSeg sg;
     while (run && rows_next_seg(pc, p1, XS, H2, sg)) {
@@ -354,18 +364,26 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
         }
         tc_fence_after();
         const long long tw2 = ROWS_CLOCK();
+#ifdef SCV_ROWS_PROF
+        if (t > 0) t_hand += tw2 - *reinterpret_cast<volatile long long*>(s_extra + 64);
+#endif
         // ---- (3) issue
         if (elect_one()) {
           uint32_t sc = s0;
           for (int ch = 0; ch < chunks; ++ch) {
-            const uint64_t da0 = desc_hi | (slab0_desc + sc * static_cast<uint32_t>(SLAB_STRIDE >> 4));
+            const uint32_t da0 = slab0_desc + sc * static_cast<uint32_t>(SLAB_STRIDE >> 4);
             if (++sc == static_cast<uint32_t>(nslab)) sc = 0;
-            const uint64_t db0 = desc_hi | (w_desc + static_cast<uint32_t>((ch * 9 * WT_BLOCK) >> 4));
+            const uint32_t db0 = w_desc + static_cast<uint32_t>((ch * 9 * WT_BLOCK) >> 4);
             if (!(p.dbg & 8)) {  // (timing experiment: no MMAs)
-              rows_issue_row<KC, COUT>(da0, db0, pc0.d1, pc0.id1, pc0.d2, pc0.id2, pc0.b_off, pc0.b_wrap);
-              rows_issue_row<KC, COUT>(da0 + (ROW_BYTES >> 4), db0, pc1.d1, pc1.id1, pc1.d2, pc1.id2, pc1.b_off, pc1.b_wrap);
+              rows_issue_row<KC, COUT>(da0, db0, desc_hi, pc0.d1, pc0.id1, pc0.d2, pc0.id2, pc0.b_off, pc0.b_wrap);
+              rows_issue_row<KC, COUT>(da0 + (ROW_BYTES >> 4), db0, desc_hi, pc1.d1, pc1.id1, pc1.d2, pc1.id2, pc1.b_off,
+                                       pc1.b_wrap);
             }
           }
+#ifdef SCV_ROWS_PROF
+          t_mma += clock64() - tw2;
+          *reinterpret_cast<volatile long long*>(s_extra + 64) = clock64();  // hand-off timestamp (profiling only)
+#endif
           if (ni > 1) mbar_arrive(&turn[me + 1 == ni ? 0 : me + 1]);  // hand the token on before the (slow) commits
           sc = s0;
           for (int ch = 0; ch < chunks; ++ch) {
@@ -385,8 +403,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
     }
 #ifdef SCV_ROWS_PROF
     if ((p.dbg & 32) && blockIdx.x == 0 && lane == 0 && me < ni)
-      printf("[rows prof] issuer %d: total %lld cyc, waits+setup %lld, turn %lld, issue+commit %lld, out pairs %u\n", me,
-             ROWS_CLOCK() - t_begin, t_wait, t_turn, t_issue, opc);
+      printf("[rows prof] issuer %d: total %lld cyc, waits+setup %lld, turn %lld, issue+commit %lld (mma issue %lld), hand-off latency %lld, own pairs %u, out pairs %u\n", me,
+             ROWS_CLOCK() - t_begin, t_wait, t_turn, t_issue, t_mma, t_hand, nth, opc);
 #endif
   } else {
     // ===================== epilogue: group g takes output row pairs g, g+NG, ... =====================

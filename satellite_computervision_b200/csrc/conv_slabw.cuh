@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kSlabwThreads, 1)
           if (!run) break;
           const uint64_t db0 = umma_smem_desc(smem_u32(wring + static_cast<size_t>(bsc) * WT_BYTES), ROWB);
           const int dy = tap / 3, dx = tap - 3 * dy;
-          const uint64_t a_off = static_cast<uint64_t>(((dy * SW + dx) * ROWB) >> 4);
+          const uint32_t a_off = static_cast<uint32_t>(((dy * SW + dx) * ROWB) >> 4);
           // ---- the turn
           if (ni > 1) {
             const uint32_t par = me == 0 ? ((nth & 1) ^ 1) : (nth & 1);
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(kSlabwThreads, 1)
             for (int i = 0; i < nt; ++i) {
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k)
-                umma_bf16(tacc[i], da0[i] + a_off + 2 * k, db0 + 2 * k, IDESC, (ch | tap | k) != 0 ? 1u : 0u);
+                umma_bf16_lo_acc(tacc[i], desc_lo(da0[i]) + a_off + 2 * k, desc_lo(db0) + 2 * k, desc_hi(da0[i]), desc_hi(db0), IDESC,
+                                 (ch | tap | k) != 0 ? 1u : 0u);
             }
             if (ni > 1) mbar_arrive(&turn[me + 1 == ni ? 0 : me + 1]);  // hand the token on before the commits
             umma_commit(&b_empty[bsc]);

@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(kConvThreads)
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k)  // +32 B per k step == +2 in the descriptor's 16-byte address units
-          umma_bf16(tmem_base, da0 + 2 * k, db0 + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+          umma_bf16_lo_acc(tmem_base, desc_lo(da0) + 2 * k, desc_lo(db0) + 2 * k, desc_hi(da0), desc_hi(db0), IDESC,
+                           (it | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
       }
       __syncwarp();
@@ -647,7 +648,8 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k)  // +32 B per k step == +2 in the descriptor's 16-byte address units
-            umma_bf16(tacc, da0 + 2 * k, db0 + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+            umma_bf16_lo_acc(tacc, desc_lo(da0) + 2 * k, desc_lo(db0) + 2 * k, desc_hi(da0), desc_hi(db0), IDESC,
+                             (it | k) != 0 ? 1u : 0u);
           if (ni > 1) mbar_arrive(&turn[me + 1 == ni ? 0 : me + 1]);  // hand the token on before the commits
           umma_commit(&empty_bar[sc]);                                 // frees this smem stage once its MMAs retire
           if (it == iters - 1) umma_commit(&acc_full[a]);              // in-order pipe: the tile's last MMA retires last
@@ -880,7 +882,7 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
               const int o0 = (t0 / 3) * SW + t0 % 3, o1 = (t1 / 3) * SW + t1 % 3;  // window offsets in pixels
               const uint64_t da = umma_smem_desc_nosw(slab_addr + o0 * 16, (o1 - o0) * 16, SW * 16);
               const uint64_t db = umma_smem_desc_nosw(w_addr + t0 * WT_BYTES, WT_BYTES, 128);
-              umma_bf16(tacc, da, db, IDESC, j != 0 ? 1u : 0u);
+              umma_bf16_lo_acc(tacc, desc_lo(da), desc_lo(db), desc_hi(da), desc_hi(db), IDESC, j != 0 ? 1u : 0u);
             }
             umma_commit(&slab_empty[s]);
           }
@@ -897,9 +899,9 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
               // descriptor address fields are in 16-byte units: all offsets below are compile-time
-              const uint64_t da = da0 + static_cast<uint64_t>(((dy * SW + dx) * ROWB + k * 32) >> 4);
-              const uint64_t db = db0 + static_cast<uint64_t>((tap * WT_BYTES + k * 32) >> 4);
-              umma_bf16(tacc, da, db, IDESC, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+              const uint32_t da = desc_lo(da0) + static_cast<uint32_t>(((dy * SW + dx) * ROWB + k * 32) >> 4);
+              const uint32_t db = desc_lo(db0) + static_cast<uint32_t>((tap * WT_BYTES + k * 32) >> 4);
+              umma_bf16_lo_acc(tacc, da, db, desc_hi(da0), desc_hi(db0), IDESC, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
             }
           }
           umma_commit(&slab_empty[s]);

@@ -155,6 +155,38 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the two descriptors given as (low word, shared high word): the address / offset arithmetic of a
+// long unrolled issue sequence then stays in 32-bit integer adds instead of 64-bit add-with-carry chains in
+// the uniform datapath, which were pacing the issue of back-to-back UMMAs (conv_rows.cuh).
+__device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+// ... with a runtime accumulate flag (0: overwrite D)
+__device__ __forceinline__ void umma_bf16_lo_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi_a,
+                                                 uint32_t desc_hi_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 da, db;\n"
+      ".reg .pred p;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi_a), "r"(desc_hi_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
 // mbarrier arrive once all previously issued UMMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
