@@ -182,3 +182,10 @@ def predict_overlap_chunks(chw, predict_fn, chunk=256, depth=64):
                 out = np.zeros((H, W) + core.shape[2:], dtype=core.dtype)
             out[y:y + chunk, x:x + chunk] = core
     return out
+
+
+def raster_generate_chip_indices(H, W, buff=128, kernel=256):
+    """utils/raster_tools.py:23-46: per-side buffer, inclusive range end."""
+    ys = list(range(buff, H - (kernel + buff) + 1, kernel))
+    xs = list(range(buff, W - (kernel + buff) + 1, kernel))
+    return [(y, x) for y in ys for x in xs]

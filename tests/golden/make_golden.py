@@ -145,10 +145,31 @@ def main():
         out = build(pt, processing, array_tools)
     finally:
         sys.stdout = _stdout
+    out['raster_chip_indices'] = raster_tools_indices()
     for name, payload in out.items():
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **payload)
         print('wrote', path, os.path.getsize(path), 'bytes')
+
+
+def raster_tools_indices():
+    """raster_tools.generate_chip_indices (utils/raster_tools.py:23-46, per-side buffer): the module imports
+    rasterio / geopandas / GDAL at the top, so the function is lifted out of the unmodified source file with
+    ``ast`` and executed on its own (it is pure Python)."""
+    import ast
+    src = open(os.path.join(REF, 'raster_tools.py')).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'generate_chip_indices')
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'raster_tools.py', 'exec'), ns)
+    gen = ns['generate_chip_indices']
+    out = {}
+    cases = [(2048, 2048, 64, 256), (10980, 10980, 64, 256), (384, 384, 64, 256), (383, 640, 64, 256),
+             (512, 512, 128, 256), (1000, 700, 32, 128), (100, 100, 0, 32), (97, 131, 3, 10), (50, 50, 64, 256)]
+    for n, (H, W, buff, kernel) in enumerate(cases):
+        out[f'case{n}_params'] = np.array([H, W, buff, kernel], dtype=np.int64)
+        out[f'case{n}_indices'] = np.array(gen(H, W, buff, kernel), dtype=np.int64).reshape(-1, 2)
+    out['ncases'] = np.array(len(cases))
+    return out
 
 
 def build(pt, processing, array_tools):

@@ -200,3 +200,21 @@ def test_gee_patch_files_to_geotiff(tmp_path):
     assert len(recs) == cols * rows
     stitched = np.block([[recs[r * cols + c]['b1'].reshape(k, k) for c in range(cols)] for r in range(rows)])
     assert np.array_equal(stitched, want[..., 0])
+
+
+def test_raster_tools_per_side_buffer_grid():
+    """Per-side-buffer grid of raster_tools (N4): engine == the reference-style loop, placement bit-exact."""
+    from satellite_computervision_b200 import raster_tools
+    m, w = _mk('A', 6, 1, (32, 64), seed=9)
+    arr = (np.random.default_rng(7).random((300, 364, 6)) * 10000).astype(np.uint16)
+    spec = processing.scalar_spec(6, 10000.0)
+    buff, kernel = 16, 64
+    got = raster_tools.predict_chips(arr, m, buff, kernel, norm=spec)
+    idx = otile.raster_generate_chip_indices(300, 364, buff, kernel)
+    assert len(idx) == 4 * 5
+    want = np.zeros((300, 364))
+    for y, x in idx:
+        chip = arr[y - buff:y + kernel + buff, x - buff:x + kernel + buff]
+        p = m.predict(chip[None], norm=spec)[0]
+        want[y:y + kernel, x:x + kernel] += p[buff:buff + kernel, buff:buff + kernel, 0]
+    assert np.array_equal(got, want)

@@ -107,3 +107,18 @@ def test_foreign_models_are_rejected():
             return x
     with pytest.raises(TypeError):
         pt.predict_chips(np.zeros((500, 500, 6)), [(64, 64)], np.zeros((500, 500)), Keras())
+
+
+def test_raster_tools_chip_grid_matches_reference_golden():
+    """raster_tools.generate_chip_indices (per-side buffer) == the function lifted from the reference source."""
+    import os
+    from oracle import tiling as otile
+    from satellite_computervision_b200 import raster_tools
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'raster_chip_indices.npz'))
+    for n in range(int(z['ncases'])):
+        H, W, buff, kernel = (int(v) for v in z[f'case{n}_params'])
+        want = [tuple(int(v) for v in r) for r in z[f'case{n}_indices']]
+        assert raster_tools.generate_chip_indices(H, W, buff, kernel) == want
+        assert otile.raster_generate_chip_indices(H, W, buff, kernel) == want
+        for y, x in want:   # every chip fits, the grid reaches the last position that does
+            assert y - buff >= 0 and x - buff >= 0 and y + kernel + buff <= H and x + kernel + buff <= W
