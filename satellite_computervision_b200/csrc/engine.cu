@@ -449,7 +449,8 @@ struct scv_engine {
   int opt_profile_layers = 0;
   int opt_stages = 0;
   int opt_watchdog_ms = 2000;
-  int opt_host_super_tiles = 256;  // ... when the scene streams in from host memory (H2D / compute / D2H overlap)
+  int opt_host_super_tiles = 0;    // ... when the scene streams in from host memory (H2D / compute / D2H overlap);
+                                   // 0 = one device batch per K1 / K4 launch: compute starts after ~3 tile rows of H2D
   int opt_super_tiles = 2048;  // target tiles per K1 / K4 launch (a full 10980^2 scene = 1764 chips: x0 4.2 GB + logits 1.0 GB)
   // timing
   std::vector<cudaEvent_t> ev_pool;
@@ -1284,7 +1285,7 @@ int scv_set_option(scv_engine* e, const char* key, int value) {
   } else if (k == "watchdog_ms") e->opt_watchdog_ms = value;
   else if (k == "max_batch") e->arch.cfg.max_batch = std::max(1, value);
   else if (k == "super_tiles") e->opt_super_tiles = std::max(1, value);
-  else if (k == "host_super_tiles") e->opt_host_super_tiles = std::max(1, value);
+  else if (k == "host_super_tiles") e->opt_host_super_tiles = std::max(0, value);
   else return fail(SCV_ERR_INVALID, "unknown option '%s'", key);
   return SCV_OK;
 }
@@ -1469,7 +1470,8 @@ int scv_predict_mosaic(scv_engine* e, const void* hwc, int dtype, int H, int W, 
   // host buffers: smaller super-batches than the device-resident path, so that compute starts after a few tile
   // rows of H2D and the D2H tail after the last K4 stays short
   std::vector<std::vector<int>> supers;
-  super_batches(n, e->arch.cfg.max_batch, std::min(e->opt_super_tiles, e->opt_host_super_tiles), &supers);
+  const int host_super = e->opt_host_super_tiles > 0 ? e->opt_host_super_tiles : e->arch.cfg.max_batch;
+  super_batches(n, e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &supers);
   int t0 = 0, rows_downloaded = 0, rows_waited = 0;
   int rc = SCV_OK;
   const size_t core_w = (size_t)ncols * K;
