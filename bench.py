@@ -325,7 +325,7 @@ def main():
     if rank == 0:
         pk = peaks()
         traffic = None  # DRAM bytes of the conv launches of one step: ncu-measured bytes per chip x chips of rank 0
-        tp = os.path.join(ROOT, 'profiles', 'r01_g_conv_traffic.json')
+        tp = os.path.join(ROOT, 'profiles', 'r01_k_conv_traffic.json')
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f)['dram_bytes_per_chip'] * (r1 - r0) * len(xs)
@@ -356,7 +356,7 @@ def main():
                          'achieved': tc, 'peak': pk['tc_sustained'], 'unit': 'TFLOP/s',
                          'frac': tc / pk['tc_sustained'] if pk['tc_sustained'] else None,
                          'frac_of_burst_peak': tc / pk['tc_burst'], 'peak_burst': pk['tc_burst'], 'traffic': traffic,
-                         'traffic_source': 'profiles/r01_g_conv_traffic.json (ncu dram__bytes_read+write, per chip)',
+                         'traffic_source': 'profiles/r01_k_conv_traffic.json (ncu dram__bytes_read+write, per chip)',
                          'peak_source': pk['source'],
                          'how': 'algorithmic FLOPs (67.41 GFLOP per 384x384x6 chip) x chips of rank 0 / CUDA-event time of '
                                 'the conv launches of the last timed step'},
