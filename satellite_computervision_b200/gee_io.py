@@ -28,42 +28,28 @@ _CRC_TABLE = None
 
 
 def _crc_table():
+    """Byte-at-a-time table of the reflected Castagnoli polynomial."""
     global _CRC_TABLE
     if _CRC_TABLE is None:
-        poly = 0x82F63B78  # Castagnoli, reflected
+        poly = 0x82F63B78
         t = np.zeros(256, dtype=np.uint32)
         for i in range(256):
             c = i
             for _ in range(8):
                 c = (c >> 1) ^ (poly if c & 1 else 0)
             t[i] = c
-        # slicing-by-8 tables: t8[k][b] = crc of byte b followed by k zero bytes
-        t8 = np.zeros((8, 256), dtype=np.uint32)
-        t8[0] = t
-        for k in range(1, 8):
-            t8[k] = (t8[k - 1] >> 8) ^ t[t8[k - 1] & 0xFF]
-        _CRC_TABLE = t8
+        _CRC_TABLE = t
     return _CRC_TABLE
 
 
 def crc32c(data: bytes) -> int:
-    """CRC-32C (Castagnoli).  Patch records are ~3.5 MB, so whole 8-byte lanes are folded with numpy."""
-    t8 = _crc_table()
-    crc = 0xFFFFFFFF
+    """CRC-32C (Castagnoli).  Patch records are ~3.5 MB: long messages are split into 4096 lanes whose
+    byte-serial CRCs advance together as one numpy recurrence and are then stitched with the GF(2)
+    "append n zero bytes" operator (the zlib crc32_combine construction)."""
     mv = memoryview(data)
-    n = len(mv)
-    i = 0
-    if n >= 4096:
-        # process in 8-byte words with vectorised table lookups over chunks, carrying the crc serially
-        # through the first 4 bytes of every word (python-level loop over words is too slow, so use the
-        # linearity of CRC: crc(a ^ b) = crc(a) ^ crc(b) for equal lengths) -- fold 8 columns independently
-        # and combine with a zero-extension operator applied by repeated squaring.
-        crc = _crc32c_blocks(mv, crc)
-        return crc ^ 0xFFFFFFFF
-    t = t8[0]
-    for b in mv[i:]:
-        crc = int(t[(crc ^ b) & 0xFF]) ^ (crc >> 8)
-    return crc ^ 0xFFFFFFFF
+    if len(mv) >= 4096:
+        return _crc32c_blocks(mv, 0xFFFFFFFF) ^ 0xFFFFFFFF
+    return _crc32c_raw(mv, 0xFFFFFFFF) ^ 0xFFFFFFFF
 
 
 def _gf2_times(mat, vec):
@@ -104,7 +90,7 @@ def _zeros_operator(nbytes):
 
 
 def _crc32c_raw(mv, crc):
-    t = _crc_table()[0]
+    t = _crc_table()
     for b in mv:
         crc = int(t[(crc ^ b) & 0xFF]) ^ (crc >> 8)
     return crc
@@ -113,7 +99,7 @@ def _crc32c_raw(mv, crc):
 def _crc32c_blocks(mv, crc):
     """Split the message into K equal lanes, run the K byte-serial CRCs as one numpy recurrence (vectorised
     over lanes), then stitch the lane CRCs with the zero-extension operator."""
-    t = _crc_table()[0]
+    t = _crc_table()
     n = len(mv)
     K = 4096
     L = n // K
@@ -365,10 +351,11 @@ _TIFF_TYPES = {np.dtype('uint8'): (1, 8), np.dtype('uint16'): (1, 16), np.dtype(
                np.dtype('float64'): (3, 64)}
 
 
-def write_geotiff(path, image, transform=None, crs=None, rows_per_strip=None):
+def write_geotiff(path, image, transform=None, crs=None, rows_per_strip=None, bigtiff=None):
     """Band-interleaved-by-pixel striped GeoTIFF of an (H, W) or (H, W, C) array.  ``transform`` = the six
     affine coefficients (a, b, c, d, e, f) of ``rio.Affine`` / the mixer's ``doubleMatrix``
-    (x = a*col + b*row + c, y = d*col + e*row + f); ``crs`` = 'EPSG:n'."""
+    (x = a*col + b*row + c, y = d*col + e*row + f); ``crs`` = 'EPSG:n'; ``bigtiff`` forces (True) or forbids
+    (False) the 64-bit container, default: by size."""
     img = np.asarray(image)
     if img.ndim == 2:
         img = img[..., None]
@@ -381,7 +368,7 @@ def write_geotiff(path, image, transform=None, crs=None, rows_per_strip=None):
     if rows_per_strip is None:
         rows_per_strip = max(1, min(H, (1 << 20) // max(row_bytes, 1)))
     nstrips = (H + rows_per_strip - 1) // rows_per_strip
-    big = H * row_bytes + 16 * nstrips + 4096 >= (1 << 32) - (1 << 20)
+    big = (H * row_bytes + 16 * nstrips + 4096 >= (1 << 32) - (1 << 20)) if bigtiff is None else bool(bigtiff)
 
     # tag -> (type, values); types: 3 SHORT, 4 LONG, 12 DOUBLE, 16 LONG8
     off_t = 16 if big else 4

@@ -19,7 +19,7 @@ def test_crc32c_known_answers_and_block_path():
     assert g.crc32c(bytes(range(32))) == 0x46DD794E
     rng = np.random.default_rng(0)
     data = rng.integers(0, 256, 100_003, dtype=np.uint8).tobytes()   # lane-parallel path + ragged tail
-    t = g._crc_table()[0]
+    t = g._crc_table()
     crc = 0xFFFFFFFF
     for b in data:
         crc = int(t[(crc ^ b) & 0xFF]) ^ (crc >> 8)
@@ -167,3 +167,14 @@ def test_geotiff_rotated_transform_and_many_strips(tmp_path):
         m = tuple(im.tag_v2[34264])
         assert m[:4] == (9.0, 1.0, 0.0, 5.0) and m[4:8] == (-1.0, -9.0, 0.0, 7.0) and m[15] == 1.0
         assert tuple(im.tag_v2[34735])[4:8] == (1024, 0, 1, 2)
+
+
+def test_bigtiff_container(tmp_path):
+    """The 64-bit container (used above 4 GB) written for a small image: OpenCV's libtiff reads it back."""
+    import cv2
+    img = (np.random.default_rng(5).random((33, 47)) * 100).astype(np.float32)
+    path = g.write_geotiff(str(tmp_path / 'big.tif'), img, (10.0, 0.0, 1.0, 0.0, -10.0, 2.0), 'EPSG:32618', rows_per_strip=5, bigtiff=True)
+    raw = open(path, 'rb').read(16)
+    assert raw[:4] == b'II\x2b\x00' and raw[4:8] == b'\x08\x00\x00\x00'
+    arr = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert arr is not None and np.array_equal(arr, img)

@@ -184,3 +184,61 @@ def test_new_style_container_hand_assembled():
     d = f['layers/dense/vars/0']
     assert d.is_dataset and d.shape == (2, 3) and np.array_equal(d.read(), data)
     assert [n for n, _ in kh.read_named_weights(bytes(buf))] == ['dense/vars/0']
+
+
+def test_chunked_gzip_shuffle_dataset_hand_assembled():
+    """A chunked dataset (v1 B-tree of chunks, filter pipeline shuffle + deflate, edge chunks that overhang the
+    dataspace) assembled byte by byte: what ``h5py.create_dataset(..., compression='gzip', shuffle=True)`` writes."""
+    import struct
+    import zlib
+    data = np.arange(5 * 7, dtype=np.float32).reshape(5, 7) * 0.5
+    cdims = (4, 4)
+    buf = bytearray(b'\0' * 96)
+
+    def alloc(b):
+        while len(buf) % 8:
+            buf.append(0)
+        a = len(buf)
+        buf.extend(b)
+        return a
+
+    # chunks: shuffle (byte transpose) then deflate, like the HDF5 filter pipeline applies them on write
+    keys = []
+    for oy in range(0, 5, 4):
+        for ox in range(0, 7, 4):
+            chunk = np.zeros(cdims, np.float32)
+            part = data[oy:oy + 4, ox:ox + 4]
+            chunk[:part.shape[0], :part.shape[1]] = part
+            shuffled = np.frombuffer(chunk.tobytes(), np.uint8).reshape(-1, 4).T.tobytes()
+            comp = zlib.compress(shuffled)
+            keys.append((len(comp), (oy, ox), alloc(comp)))
+    # one leaf B-tree node of type 1: key = chunk size, filter mask, offsets (rank + 1), then child address
+    node = b'TREE' + struct.pack('<BBHQQ', 1, 0, len(keys), kh.UNDEF, kh.UNDEF)
+    for size, (oy, ox), addr in keys:
+        node += struct.pack('<IIQQQ', size, 0, oy, ox, 0) + struct.pack('<Q', addr)
+    node += struct.pack('<IIQQQ', 0, 0, 8, 8, 0)  # final key
+    btree = alloc(node)
+
+    def msg(t, body, flags=0):
+        body = body + b'\0' * (-len(body) % 8)
+        return struct.pack('<HHB3x', t, len(body), flags) + body
+
+    f32 = struct.pack('<BBBBI', 0x11, 0x20, 31, 0, 4) + struct.pack('<HHBBBBI', 0, 32, 23, 8, 0, 23, 127)
+    space = struct.pack('<BBB5x', 1, 2, 0) + struct.pack('<QQ', 5, 7)
+    layout = struct.pack('<BBB', 3, 2, 3) + struct.pack('<Q', btree) + struct.pack('<III', 4, 4, 4)
+    # filter pipeline v1: shuffle (id 2, one client value = element size), deflate (id 1, level)
+    def filt(fid, name, cvals):
+        nm = name + b'\0' * (-len(name) % 8)
+        b = struct.pack('<HHHH', fid, len(nm), 1, len(cvals)) + nm + b''.join(struct.pack('<I', v) for v in cvals)
+        return b + (b'\0' * 4 if len(cvals) % 2 else b'')
+    pipeline = struct.pack('<BB6x', 1, 2) + filt(2, b'shuffle\0', [4]) + filt(1, b'deflate\0', [4])
+    msgs = [msg(0x01, space), msg(0x03, f32, 1), msg(0x08, layout), msg(0x0B, pipeline)]
+    body = b''.join(msgs)
+    dset = alloc(struct.pack('<BxHII4x', 1, len(msgs), 1, len(body)) + body)
+    w = kh._Writer()
+    w.buf = buf                      # reuse the old-style group writer for the root group around the raw dataset
+    root = w.group({'kernel': dset})
+    f = kh.H5File(w.finish(root))
+    d = f['kernel']
+    assert d.shape == (5, 7) and d.layout[0] == 'chunked' and [fid for fid, _ in d.filters] == [2, 1]
+    assert np.array_equal(d.read(), data)
