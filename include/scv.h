@@ -67,7 +67,15 @@ enum {
    * (notebooks/UNET_G4G_2019_solar.ipynb:808-820, :1541); eps = div[0]. */
   SCV_NORM_TILE_ZSCORE = 4,
   /* rescale_tensor axes=[0,1]: per-tile per-band min/max; eps = div[0]. */
-  SCV_NORM_TILE_MINMAX = 5
+  SCV_NORM_TILE_MINMAX = 5,
+  /* pc_tools.normalize_dataArray(da, 'band') (utils/pc_tools.py:90-107, applied to the mosaic at
+   * utils/prediction_tools.py:757-758): per pixel across bands, NaN-skipping mean and population
+   * standard deviation, (x - mean) / (sd + eps); eps = div[0] (1e-6 in the reference).  A NaN band stays NaN. */
+  SCV_NORM_PIXEL_ZSCORE_SD = 6,
+  /* rescale_tensor axes=[0,1,2] (utils/processing.py:307-308): ONE min/max per tile (per channel group). */
+  SCV_NORM_TILE_GLOBAL_MINMAX = 7,
+  /* normalize_tensor axes=[0,1,2] (:257): ONE mean/variance per tile (per channel group). */
+  SCV_NORM_TILE_GLOBAL_ZSCORE = 8
 };
 
 /* Architecture = arguments of model_tools.get_unet_model (utils/model_tools.py:394)
@@ -99,6 +107,13 @@ typedef struct {
   int nbands;
   float sub[SCV_MAX_BANDS];
   float div[SCV_MAX_BANDS];
+  /* data-derived modes (every mode except NONE / PER_BAND): `splits=` of rescale_tensor / normalize_tensor
+   * (utils/processing.py:314-318, :267-275) -- contiguous channel groups normalised independently.
+   * ngroups == 0: one group of all nbands.  Channels beyond sum(group_size) pass through unchanged
+   * (normalize_tensor :269-274; derived / one-hot planes appended by make_pred_dataset,
+   * utils/prediction_tools.py:198-215). */
+  int ngroups;
+  int group_size[SCV_MAX_BANDS];
 } scv_norm;
 
 /* generate_chip_indices(arr, buff, kernel), utils/prediction_tools.py:87-109 */
@@ -106,6 +121,26 @@ typedef struct {
   int kernel; /* kept core side (256)                       */
   int buff;   /* TOTAL buffer (128): buff/2 trimmed per side */
 } scv_tiling;
+
+/* Options of the extended mosaic calls.  Zero-initialised == the plain calls on the whole chip list. */
+typedef struct {
+  int tile_begin, tile_end; /* chips [begin, end) of the row-major chip list of generate_chip_indices
+                               (tile-balanced multi-GPU sharding); end <= 0: to the last chip */
+  int out_channel;          /* probability channel stitched (0 as at prediction_tools.py:154; 1 as at :267) */
+  int out_dtype;            /* element type of out_prob: 0 / SCV_F32 or SCV_F64 (the reference's template is
+                               float64 zeros, utils/prediction_tools.py:769)                                 */
+  int accumulate;           /* 1: out_prob[core] += p like predict_chips (:154); 0: assign                  */
+  int valid[4];             /* y0, y1, x0, x1 (exclusive ends), mosaic coordinates: pixels outside this window
+                               are fed to the network as exact zeros AFTER normalisation (dask map_overlap
+                               boundary=0 pads the already normalised raster, utils/prediction_tools.py:823-829);
+                               all zero: the whole mosaic is valid                                          */
+} scv_mosaic_opts;
+
+/* crop window of the patch-list stitchers (utils/prediction_tools.py:258-261, :340-343, :496-520): patch i keeps
+ * rows [y0, y0+h) and columns [x0, x0+w) and lands at row (i / cols) * h, column (i % cols) * w. */
+typedef struct {
+  int y0, x0, h, w;
+} scv_crop;
 
 /* per-call device timings of the last predict call, milliseconds (CUDA events) */
 typedef struct {
@@ -174,6 +209,28 @@ SCV_API int scv_predict_patches(scv_engine* e, const void* nhwc, int dtype, int 
                         const scv_tiling* tiling, const scv_norm* norm, int cols, int out_channel,
                         float* out_prob, uint8_t* out_mask);
 
+/* scv_predict_mosaic with chip-range sharding, float64 / accumulating output and a valid window (see
+ * scv_mosaic_opts).  out_prob is H*W elements of opts->out_dtype.  Host buffers that are not page-locked are
+ * registered for the duration of the call (cudaHostRegister) so the copies overlap the compute. */
+SCV_API int scv_predict_mosaic_ex(scv_engine* e, const void* hwc, int dtype, int H, int W, int C,
+                          const scv_tiling* tiling, const scv_norm* norm, const scv_mosaic_opts* opts,
+                          void* out_prob, uint8_t* out_mask);
+
+/* Streaming form of scv_predict_mosaic_ex for sustained multi-scene throughput (BASELINE configs[4]): returns
+ * as soon as the scene's copies and kernels are enqueued; up to two scenes are in flight per engine, scene i+1's
+ * H2D overlapping scene i's compute and scene i's D2H overlapping scene i+1's compute.  hwc / out_prob /
+ * out_mask must be page-locked (scv_host_alloc) and stay valid until scv_stream_wait(ticket) returns. */
+SCV_API int scv_stream_submit(scv_engine* e, const void* hwc, int dtype, int H, int W, int C,
+                      const scv_tiling* tiling, const scv_norm* norm, const scv_mosaic_opts* opts, void* out_prob,
+                      uint8_t* out_mask, int* ticket);
+/* Blocks until scene `ticket` (ticket < 0: every submitted scene) is complete in host memory. */
+SCV_API int scv_stream_wait(scv_engine* e, int ticket);
+
+/* scv_predict_patches with an arbitrary crop window (non-square kernel_buffer, utils/prediction_tools.py:258-261). */
+SCV_API int scv_predict_patches_ex(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C,
+                           const scv_crop* crop, const scv_norm* norm, int cols, int out_channel, float* out_prob,
+                           uint8_t* out_mask);
+
 /* ---- predict: device-resident buffers (bench `value`, multi-GPU sharding) --- */
 
 /* Same as scv_predict_mosaic but d_hwc / d_prob / d_mask are DEVICE pointers.
@@ -186,7 +243,17 @@ SCV_API int scv_predict_mosaic_device(scv_engine* e, const void* d_hwc, int dtyp
                               int tile_row_begin, int tile_row_end, int out_channel, float* d_prob,
                               uint8_t* d_mask, int dst_row0, void* stream);
 
+/* ... with scv_mosaic_opts (chip-range sharding; out_dtype / accumulate apply to d_prob). */
+SCV_API int scv_predict_mosaic_device_ex(scv_engine* e, const void* d_hwc, int dtype, int H, int W, int C,
+                                 int src_row0, const scv_tiling* tiling, const scv_norm* norm,
+                                 const scv_mosaic_opts* opts, void* d_prob, uint8_t* d_mask, int dst_row0,
+                                 void* stream);
+
 SCV_API int scv_get_times(scv_engine* e, scv_times* out);
+/* Reads (and clears) the engine's device-side error word: SCV_ERR_KERNEL if a watchdog tripped in any launch
+ * since the last check -- for callers of the stream-taking device entry points, which return before the
+ * kernels have run. */
+SCV_API int scv_check(scv_engine* e);
 
 /* pinned host memory for overlap-capable H2D/D2H (cudaHostAlloc) */
 SCV_API void* scv_host_alloc(size_t bytes);

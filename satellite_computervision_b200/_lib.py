@@ -13,7 +13,7 @@ SCV_MAX_LEVELS, SCV_MAX_BANDS, SCV_MAX_CLASSES, SCV_MAX_LAYERS = 8, 16, 16, 64
 SCV_U8, SCV_U16, SCV_I16, SCV_F32, SCV_F64 = range(5)
 SCV_HEAD_SIGMOID, SCV_HEAD_SOFTMAX = 0, 1
 (SCV_NORM_NONE, SCV_NORM_PER_BAND, SCV_NORM_PIXEL_MINMAX, SCV_NORM_PIXEL_ZSCORE, SCV_NORM_TILE_ZSCORE,
- SCV_NORM_TILE_MINMAX) = range(6)
+ SCV_NORM_TILE_MINMAX, SCV_NORM_PIXEL_ZSCORE_SD, SCV_NORM_TILE_GLOBAL_MINMAX, SCV_NORM_TILE_GLOBAL_ZSCORE) = range(9)
 SCV_OK, SCV_ERR_INVALID, SCV_ERR_CUDA, SCV_ERR_STATE, SCV_ERR_KERNEL = 0, -1, -2, -3, -4
 
 DTYPES = {np.dtype('uint8'): SCV_U8, np.dtype('uint16'): SCV_U16, np.dtype('int16'): SCV_I16,
@@ -40,11 +40,20 @@ class Tensor(C.Structure):
 
 class Norm(C.Structure):
     _fields_ = [('mode', C.c_int), ('nbands', C.c_int), ('sub', C.c_float * SCV_MAX_BANDS),
-                ('div', C.c_float * SCV_MAX_BANDS)]
+                ('div', C.c_float * SCV_MAX_BANDS), ('ngroups', C.c_int), ('group_size', C.c_int * SCV_MAX_BANDS)]
 
 
 class Tiling(C.Structure):
     _fields_ = [('kernel', C.c_int), ('buff', C.c_int)]
+
+
+class MosaicOpts(C.Structure):
+    _fields_ = [('tile_begin', C.c_int), ('tile_end', C.c_int), ('out_channel', C.c_int), ('out_dtype', C.c_int),
+                ('accumulate', C.c_int), ('valid', C.c_int * 4)]
+
+
+class Crop(C.Structure):
+    _fields_ = [('y0', C.c_int), ('x0', C.c_int), ('h', C.c_int), ('w', C.c_int)]
 
 
 class Times(C.Structure):
@@ -71,6 +80,16 @@ PROTOTYPES = {
                                      C.c_int, C.c_int, C.c_int, _P, _P]),
     'scv_predict_patches': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Tiling),
                                       C.POINTER(Norm), C.c_int, C.c_int, _P, _P]),
+    'scv_predict_mosaic_ex': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Tiling), C.POINTER(Norm),
+                                        C.POINTER(MosaicOpts), _P, _P]),
+    'scv_stream_submit': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Tiling), C.POINTER(Norm),
+                                    C.POINTER(MosaicOpts), _P, _P, C.POINTER(C.c_int)]),
+    'scv_stream_wait': (C.c_int, [_P, C.c_int]),
+    'scv_predict_patches_ex': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Crop),
+                                         C.POINTER(Norm), C.c_int, C.c_int, _P, _P]),
+    'scv_predict_mosaic_device_ex': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Tiling),
+                                               C.POINTER(Norm), C.POINTER(MosaicOpts), _P, _P, C.c_int, _P]),
+    'scv_check': (C.c_int, [_P]),
     'scv_predict_mosaic_device': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Tiling),
                                             C.POINTER(Norm), C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     'scv_get_times': (C.c_int, [_P, C.POINTER(Times)]),
@@ -142,6 +161,33 @@ def pinned_empty(shape, dtype):
 
 
 _PINNED = {}
+
+
+class _PinnedOwner:
+    def __init__(self, p):
+        self.p = p
+
+    def __del__(self):
+        try:
+            if self.p and _LIB is not None:
+                _LIB.scv_host_free(self.p)
+        except Exception:
+            pass
+
+
+def pinned_zeros(shape, dtype):
+    """Zero-filled page-locked array whose memory is released with the array (results handed to callers)."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    n = max(count * dtype.itemsize, 1)
+    p = lib.scv_host_alloc(n)
+    if not p:
+        raise ScvError(SCV_ERR_CUDA, lib.scv_last_error().decode())
+    C.memset(p, 0, n)
+    buf = (C.c_uint8 * n).from_address(p)
+    buf._scv_owner = _PinnedOwner(p)  # every view's .base chain ends at `buf`: the memory lives as long as any view
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 def pinned_free(arr):

@@ -148,10 +148,13 @@ cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   return cudaErrorInvalidValue;
 }
 
+// cudaFuncSetAttribute is per device: one engine per GPU and several engines per process must each opt in.
 cudaError_t conv_init_attributes() {
-  static bool done = false;
-  if (done) return cudaSuccess;
-  cudaError_t e;
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
   if ((e = attr_kc8<32>()) != cudaSuccess) return e;
   if ((e = attr_kc8<64>()) != cudaSuccess) return e;
   if ((e = attr_kc8<128>()) != cudaSuccess) return e;
@@ -160,7 +163,7 @@ cudaError_t conv_init_attributes() {
   if ((e = attr_bn<64>()) != cudaSuccess) return e;
   if ((e = conv_rows_init_attributes()) != cudaSuccess) return e;
   if ((e = conv_slabw_init_attributes()) != cudaSuccess) return e;
-  done = true;
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }
 

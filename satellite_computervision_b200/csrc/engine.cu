@@ -424,15 +424,32 @@ struct scv_engine {
   int* d_err = nullptr;
   cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
   std::vector<std::unique_ptr<Plan>> plans;
+  // host-buffer mosaic calls: two scene slots so that streamed scenes overlap (scv_stream_submit)
+  struct Slot {
+    void* d_scene = nullptr;
+    size_t scene_bytes = 0;
+    void* d_prob = nullptr;
+    size_t prob_bytes = 0;
+    uint8_t* d_mask = nullptr;
+    size_t mask_bytes = 0;
+    cudaEvent_t compute_done = nullptr, d2h_done = nullptr;
+    std::vector<cudaEvent_t> up_ev, row_ev;  // per tile row: H2D landed / kernels done (reused across scenes)
+    std::vector<void*> registered;           // host ranges page-locked for the scene in flight
+    int ticket = -1;
+    bool busy = false;
+  };
+  Slot slots[2];
+  int next_ticket = 0;
   // scratch
-  void* d_scene = nullptr;
-  size_t scene_bytes = 0;
-  float* d_prob = nullptr;
+  float* d_prob = nullptr;  // patch-list rasters
   size_t prob_bytes = 0;
   uint8_t* d_mask = nullptr;
   size_t mask_bytes = 0;
   int2* d_origins = nullptr;
   size_t origins_cap = 0;
+  std::vector<int2> h_origins;
+  long long origins_key[8] = {};
+  bool origins_valid = false;
   float* d_tile_stats = nullptr;
   size_t tile_stats_cap = 0;
   void* d_stage = nullptr;  // raw tiles staging for predict_tiles / predict_patches
@@ -451,6 +468,7 @@ struct scv_engine {
   int opt_watchdog_ms = 2000;
   int opt_host_super_tiles = 0;    // ... when the scene streams in from host memory (H2D / compute / D2H overlap);
                                    // 0 = one device batch per K1 / K4 launch: compute starts after ~3 tile rows of H2D
+  int opt_host_register = 1;       // page-lock pageable caller buffers for the duration of a host-buffer mosaic call
   int opt_super_tiles = 2048;  // target tiles per K1 / K4 launch (a full 10980^2 scene = 1764 chips: x0 4.2 GB + logits 1.0 GB)
   // timing
   std::vector<cudaEvent_t> ev_pool;
@@ -605,13 +623,14 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+static int sm_count() {  // of the CURRENT device (engines on different GPUs may share a process)
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
   return n;
 }
 
@@ -971,33 +990,52 @@ struct TileJob {
   int side;
   const int2* d_src_origins;  // n tiles
   const scv_norm* norm;
+  int valid[4];               // y0, y1, x0, x1 of the valid window (y1 <= y0: none)
+  int order_kernel, tiles_per_row, order_skip0;  // regular chip grid: K1 block ordering (order_kernel == 0: off)
   // destination: stitched raster ...
   const int2* d_dst_origins;  // n tiles (null -> per-tile outputs)
-  int kernel, crop, out_W, dst_row0, out_channel, force_scalar;
-  float* d_prob;
+  int kernel_h, kernel_w, crop_y, crop_x, out_W, dst_row0, out_channel, force_scalar;
+  void* d_prob;
+  int prob_f64, accumulate;
   uint8_t* d_mask;
   // ... or whole tiles
   float* d_tile_probs;
   int32_t* d_tile_classes;
 };
 
+static bool tile_stats_mode(int m) {
+  return m == SCV_NORM_TILE_ZSCORE || m == SCV_NORM_TILE_MINMAX || m == SCV_NORM_TILE_GLOBAL_ZSCORE ||
+         m == SCV_NORM_TILE_GLOBAL_MINMAX;
+}
+
 static int norm_to_params(const scv_norm* n, int C, ExtractParams* ep) {
   ep->norm_mode = n ? n->mode : SCV_NORM_NONE;
+  ep->ngroups = 0;
   for (int c = 0; c < SCV_MAX_BANDS; ++c) {
     ep->sub[c] = 0.f;
     ep->div[c] = 1.f;
+    ep->group_end[c] = 0;
   }
   if (!n || n->mode == SCV_NORM_NONE) return SCV_OK;
-  if (n->mode < 0 || n->mode > SCV_NORM_TILE_MINMAX) return fail(SCV_ERR_INVALID, "unknown norm mode %d", n->mode);
+  if (n->mode < 0 || n->mode > SCV_NORM_TILE_GLOBAL_ZSCORE) return fail(SCV_ERR_INVALID, "unknown norm mode %d", n->mode);
   if (n->mode == SCV_NORM_PER_BAND) {
     if (n->nbands != C) return fail(SCV_ERR_INVALID, "norm has %d bands, input has %d", n->nbands, C);
     for (int c = 0; c < C; ++c) {
       ep->sub[c] = n->sub[c];
       ep->div[c] = n->div[c];
     }
-  } else {
-    ep->div[0] = n->div[0];  // epsilon
+    return SCV_OK;
   }
+  ep->div[0] = n->div[0];  // epsilon
+  if (n->ngroups < 0 || n->ngroups > SCV_MAX_BANDS) return fail(SCV_ERR_INVALID, "norm: ngroups %d out of range", n->ngroups);
+  int end = 0;
+  for (int g = 0; g < n->ngroups; ++g) {
+    if (n->group_size[g] <= 0) return fail(SCV_ERR_INVALID, "norm: group %d has size %d", g, n->group_size[g]);
+    end += n->group_size[g];
+    ep->group_end[g] = end;
+  }
+  if (end > C) return fail(SCV_ERR_INVALID, "norm: channel groups cover %d bands, input has %d", end, C);
+  ep->ngroups = n->ngroups;
   return SCV_OK;
 }
 
@@ -1047,10 +1085,18 @@ static int run_super(scv_engine* e, const TileJob& job, int t0, const std::vecto
   ep.side = job.side;
   ep.cpad = a.c0pad;
   SCV_TRY(norm_to_params(job.norm, job.C, &ep));
+  ep.valid_y0 = job.valid[0], ep.valid_y1 = job.valid[1], ep.valid_x0 = job.valid[2], ep.valid_x1 = job.valid[3];
+  if (job.order_kernel > 0) {
+    ep.order_kernel = job.order_kernel;
+    ep.tiles_per_row = job.tiles_per_row;
+    ep.order_skip = (job.order_skip0 + t0) % job.tiles_per_row;
+  }
   const int row_bytes = job.side * job.C * dtype_bytes(job.dtype);
   ep.rows_per_block = std::max(1, std::min(8, (44 * 1024) / (row_bytes + 32)));
   ep.out = e->d_x0_all;
-  if (ep.norm_mode == SCV_NORM_TILE_ZSCORE || ep.norm_mode == SCV_NORM_TILE_MINMAX) {
+  if (tile_stats_mode(ep.norm_mode)) {
+    if (ep.valid_y1 > ep.valid_y0)
+      return fail(SCV_ERR_INVALID, "per-tile statistics cannot be combined with a valid window (the padding would enter the statistics)");
     SCV_TRY(ensure((void**)&e->d_tile_stats, &e->tile_stats_cap, (size_t)n * job.C * 2 * sizeof(float)));
     TileStatsParams sp{};
     sp.src = ep.src;
@@ -1063,6 +1109,8 @@ static int run_super(scv_engine* e, const TileJob& job, int t0, const std::vecto
     sp.mode = ep.norm_mode;
     sp.eps = ep.div[0];
     sp.stats = e->d_tile_stats;
+    sp.ngroups = ep.ngroups;
+    for (int c = 0; c < SCV_MAX_BANDS; ++c) sp.group_end[c] = ep.group_end[c];
     CUDA_TRY(launch_tile_stats(sp, n, s));
     e->n_launches++;
     ep.tile_stats = e->d_tile_stats;
@@ -1089,13 +1137,17 @@ static int run_super(scv_engine* e, const TileJob& job, int t0, const std::vecto
     sp.head = a.cfg.head;
     sp.threshold = a.cfg.threshold;
     sp.out_channel = job.out_channel;
-    sp.crop = job.crop;
-    sp.kernel = job.kernel;
+    sp.crop_y = job.crop_y;
+    sp.crop_x = job.crop_x;
+    sp.kernel_h = job.kernel_h;
+    sp.kernel_w = job.kernel_w;
     sp.dst_origins = job.d_dst_origins + t0;
     sp.force_scalar = job.force_scalar;
     sp.dst_row0 = job.dst_row0;
     sp.out_W = job.out_W;
     sp.prob = job.d_prob;
+    sp.prob_f64 = job.prob_f64;
+    sp.accumulate = job.accumulate;
     sp.mask = job.d_mask;
     CUDA_TRY(launch_stitch(sp, n, s));
   } else {
@@ -1116,9 +1168,6 @@ static int run_super(scv_engine* e, const TileJob& job, int t0, const std::vecto
   return SCV_OK;
 }
 
-// Groups the balanced device batches of `n` tiles into super-batches of roughly `target` tiles.
-static void super_batches(int n, int maxb, int target, std::vector<std::vector<int>>* out);
-
 static void balanced_batches(int n, int maxb, std::vector<int>* sizes) {
   sizes->clear();
   if (n <= 0) return;
@@ -1127,6 +1176,7 @@ static void balanced_batches(int n, int maxb, std::vector<int>* sizes) {
   for (int i = 0; i < nb; ++i) sizes->push_back(base + (i < extra ? 1 : 0));
 }
 
+// Groups the balanced device batches of `n` tiles into super-batches of roughly `target` tiles.
 static void super_batches(int n, int maxb, int target, std::vector<std::vector<int>>* out) {
   std::vector<int> sizes;
   balanced_batches(n, maxb, &sizes);
@@ -1143,13 +1193,6 @@ static void super_batches(int n, int maxb, int target, std::vector<std::vector<i
   }
 }
 
-// generate_chip_indices (utils/prediction_tools.py:87-109): y in range(buff/2, H-(buff+kernel), kernel)
-static void chip_grid(int H, int W, const scv_tiling* t, std::vector<int>* ys, std::vector<int>* xs) {
-  const int side = t->buff + t->kernel, half = t->buff / 2;
-  for (int y = half; y < H - side; y += t->kernel) ys->push_back(y);
-  for (int x = half; x < W - side; x += t->kernel) xs->push_back(x);
-}
-
 static int check_tiling(const scv_engine* e, const scv_tiling* t) {
   if (!t || t->kernel <= 0 || t->buff < 0 || (t->buff & 1))
     return fail(SCV_ERR_INVALID, "tiling: kernel must be > 0 and buff a non-negative even number");
@@ -1159,10 +1202,115 @@ static int check_tiling(const scv_engine* e, const scv_tiling* t) {
   return SCV_OK;
 }
 
+// Chip list of a mosaic call: generate_chip_indices (utils/prediction_tools.py:87-109,
+// y in range(buff/2, H-(buff+kernel), kernel)) restricted to the chip range [tb, te) of its row-major order.
+struct MosaicGeom {
+  std::vector<int> ys, xs;
+  int half, side, K, ncols;
+  int tb, te;          // chip range
+  int r_first, r_last; // tile rows touched (inclusive)
+  int n() const { return te - tb; }
+  int c0(int r) const { return r == r_first ? tb % ncols : 0; }                 // first chip column of tile row r
+  int c1(int r) const { return r == r_last ? (te - 1) % ncols + 1 : ncols; }    // one past the last
+};
+
+static int mosaic_geom(const scv_engine* e, int H, int W, const scv_tiling* t, const scv_mosaic_opts* o, MosaicGeom* g) {
+  SCV_TRY(check_tiling(e, t));
+  g->side = t->buff + t->kernel;
+  g->half = t->buff / 2;
+  g->K = t->kernel;
+  g->ys.clear();
+  g->xs.clear();
+  for (int y = g->half; y < H - g->side; y += t->kernel) g->ys.push_back(y);
+  for (int x = g->half; x < W - g->side; x += t->kernel) g->xs.push_back(x);
+  g->ncols = (int)g->xs.size();
+  const int total = (int)g->ys.size() * g->ncols;
+  g->tb = o ? std::max(0, o->tile_begin) : 0;
+  g->te = (o && o->tile_end > 0) ? std::min(o->tile_end, total) : total;
+  if (g->tb >= g->te) {
+    g->tb = g->te = 0;  // empty chip list: nothing predicted
+    g->r_first = 0, g->r_last = -1;
+    return SCV_OK;
+  }
+  g->r_first = g->tb / g->ncols;
+  g->r_last = (g->te - 1) / g->ncols;
+  return SCV_OK;
+}
+
+static int check_opts(const scv_engine* e, const scv_mosaic_opts* o) {
+  if (!o) return SCV_OK;
+  if (o->out_channel < 0 || o->out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", o->out_channel);
+  if (o->out_dtype != 0 && o->out_dtype != SCV_F32 && o->out_dtype != SCV_F64)
+    return fail(SCV_ERR_INVALID, "out_dtype must be SCV_F32 or SCV_F64");
+  return SCV_OK;
+}
+
+// Uploads the chip origins of `g` ([n source origins][n destination origins]) unless the same list is already
+// resident (repeated calls on one geometry: no per-call upload, no synchronisation).
+static int upload_origins(scv_engine* e, const MosaicGeom& g, int H, int W, cudaStream_t s, int* force_scalar) {
+  const int n = g.n();
+  long long key[8] = {H, W, g.K, g.half, g.tb, g.te, 1, 0};
+  int fs = 0;
+  for (int x : g.xs) fs |= (x & 3) ? 3 : ((x & 7) ? 2 : 0);
+  *force_scalar = fs;
+  if (e->origins_valid && memcmp(key, e->origins_key, sizeof key) == 0) return SCV_OK;
+  e->h_origins.resize(2 * (size_t)n);
+  for (int k = 0; k < n; ++k) {
+    const int t = g.tb + k, r = t / g.ncols, c = t % g.ncols;
+    e->h_origins[k] = make_int2(g.xs[c] - g.half, g.ys[r] - g.half);
+    e->h_origins[n + k] = make_int2(g.xs[c], g.ys[r]);
+  }
+  e->origins_valid = false;
+  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, e->h_origins.size() * sizeof(int2)));
+  // pageable source: the runtime stages it before returning, so h_origins may be rewritten by the next call
+  CUDA_TRY(cudaMemcpyAsync(e->d_origins, e->h_origins.data(), e->h_origins.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+  if (s == e->stream) {  // a caller-supplied stream gives no ordering against later calls on other streams
+    memcpy(e->origins_key, key, sizeof key);
+    e->origins_valid = true;
+  }
+  return SCV_OK;
+}
+
+static void fill_mosaic_job(TileJob* job, const MosaicGeom& g, int dtype, int W, int C, const scv_norm* norm,
+                            const scv_mosaic_opts* o, int force_scalar, const int2* d_origins) {
+  job->dtype = dtype;
+  job->src_W = W;
+  job->C = C;
+  job->side = g.side;
+  job->d_src_origins = d_origins;
+  job->norm = norm;
+  job->d_dst_origins = d_origins + g.n();
+  job->kernel_h = job->kernel_w = g.K;
+  job->crop_y = job->crop_x = g.half;
+  job->out_W = W;
+  job->out_channel = o ? o->out_channel : 0;
+  job->force_scalar = force_scalar;
+  job->prob_f64 = (o && o->out_dtype == SCV_F64) ? 1 : 0;
+  job->accumulate = (o && o->accumulate) ? 1 : 0;
+  if (o) memcpy(job->valid, o->valid, sizeof job->valid);
+  job->order_kernel = g.K <= g.side ? g.K : 0;
+  job->tiles_per_row = g.ncols;
+  job->order_skip0 = g.tb % std::max(1, g.ncols);
+}
+
+// RAII: the API must not change the caller's (e.g. torch's) current device behind its back
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // =================================================================== C ABI
 extern "C" {
 
-const char* scv_version(void) { return "scv-b200 0.1 (sm_100a, tcgen05/TMEM/TMA)"; }
+const char* scv_version(void) { return "scv-b200 0.2 (sm_100a, tcgen05/TMEM/TMA)"; }
 const char* scv_last_error(void) { return g_err.c_str(); }
 
 int scv_device_count(void) {
@@ -1203,6 +1351,7 @@ int scv_engine_create(const scv_config* cfg, scv_engine** out) {
     return fail(SCV_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
   }
   if (cfg->device < 0 || cfg->device >= ndev) return fail(SCV_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(cfg->device));
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1217,12 +1366,22 @@ int scv_engine_create(const scv_config* cfg, scv_engine** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&e->d_err, sizeof(int)));
   CUDA_TRY(cudaMemset(e->d_err, 0, sizeof(int)));
+  for (auto& sl : e->slots) {
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+  }
   *out = e.release();
   return SCV_OK;
 }
 
+static void slot_release_host(scv_engine::Slot& sl) {
+  for (void* p : sl.registered) cudaHostUnregister(p);
+  sl.registered.clear();
+}
+
 void scv_engine_destroy(scv_engine* e) {
   if (!e) return;
+  DeviceGuard guard;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   reset_timing(e);
@@ -1233,10 +1392,19 @@ void scv_engine_destroy(scv_engine* e) {
     cudaFree(l.d_skip_s);
     cudaFree(l.d_skip_t);
   }
+  for (auto& sl : e->slots) {
+    slot_release_host(sl);
+    cudaFree(sl.d_scene);
+    cudaFree(sl.d_prob);
+    cudaFree(sl.d_mask);
+    for (auto ev : sl.up_ev) cudaEventDestroy(ev);
+    for (auto ev : sl.row_ev) cudaEventDestroy(ev);
+    if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+    if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+  }
   cudaFree(e->d_head_w);
   cudaFree(e->d_head_b);
   cudaFree(e->d_err);
-  cudaFree(e->d_scene);
   cudaFree(e->d_prob);
   cudaFree(e->d_mask);
   cudaFree(e->d_origins);
@@ -1254,6 +1422,7 @@ void scv_engine_destroy(scv_engine* e) {
 
 int scv_engine_set_weights(scv_engine* e, const scv_tensor* tensors, int n) {
   if (!e || !tensors) return fail(SCV_ERR_INVALID, "NULL argument");
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(e->device));
   const auto& specs = e->arch.specs;
   if (n != (int)specs.size()) return fail(SCV_ERR_INVALID, "expected %d weight arrays, got %d", (int)specs.size(), n);
@@ -1264,7 +1433,7 @@ int scv_engine_set_weights(scv_engine* e, const scv_tensor* tensors, int n) {
       if (tensors[i].shape[d] != specs[i].shape[d])
         return fail(SCV_ERR_INVALID, "weight %d (%s): dim %d is %lld, expected %lld", i, specs[i].name.c_str(), d, (long long)tensors[i].shape[d], (long long)specs[i].shape[d]);
   }
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  CUDA_TRY(cudaDeviceSynchronize());
   SCV_TRY(fold_and_upload(e, tensors));
   // weight pointers / tensor maps are baked into the plans
   for (auto& pl : e->plans) cudaFree(pl->arena);
@@ -1275,6 +1444,8 @@ int scv_engine_set_weights(scv_engine* e, const scv_tensor* tensors, int n) {
 
 int scv_set_option(scv_engine* e, const char* key, int value) {
   if (!e || !key) return fail(SCV_ERR_INVALID, "NULL argument");
+  DeviceGuard guard;
+  cudaSetDevice(e->device);
   const std::string k(key);
   if (k == "profile_layers") e->opt_profile_layers = value;
   else if (k == "stages") {
@@ -1286,21 +1457,31 @@ int scv_set_option(scv_engine* e, const char* key, int value) {
   else if (k == "max_batch") e->arch.cfg.max_batch = std::max(1, value);
   else if (k == "super_tiles") e->opt_super_tiles = std::max(1, value);
   else if (k == "host_super_tiles") e->opt_host_super_tiles = std::max(0, value);
+  else if (k == "host_register") e->opt_host_register = value;
   else return fail(SCV_ERR_INVALID, "unknown option '%s'", key);
   return SCV_OK;
 }
 
 int scv_get_times(scv_engine* e, scv_times* out) {
   if (!e || !out) return fail(SCV_ERR_INVALID, "NULL argument");
+  DeviceGuard guard;
   CUDA_TRY(cudaSetDevice(e->device));
   SCV_TRY(finalize_times(e));
   *out = e->times;
   return SCV_OK;
 }
 
+int scv_check(scv_engine* e) {
+  if (!e) return fail(SCV_ERR_INVALID, "engine is NULL");
+  DeviceGuard guard;
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return check_device_err(e);
+}
+
 void* scv_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
     cudaGetLastError();
     g_err = "cudaHostAlloc failed";
     return nullptr;
@@ -1320,64 +1501,35 @@ static int precheck(scv_engine* e, int dtype, int C) {
   return SCV_OK;
 }
 
-int scv_predict_mosaic_device(scv_engine* e, const void* d_hwc, int dtype, int H, int W, int C, int src_row0,
-                              const scv_tiling* tiling, const scv_norm* norm, int tile_row_begin, int tile_row_end,
-                              int out_channel, float* d_prob, uint8_t* d_mask, int dst_row0, void* stream) {
+int scv_predict_mosaic_device_ex(scv_engine* e, const void* d_hwc, int dtype, int H, int W, int C, int src_row0,
+                                 const scv_tiling* tiling, const scv_norm* norm, const scv_mosaic_opts* opts,
+                                 void* d_prob, uint8_t* d_mask, int dst_row0, void* stream) {
+  DeviceGuard guard;
   SCV_TRY(precheck(e, dtype, C));
-  SCV_TRY(check_tiling(e, tiling));
+  SCV_TRY(check_opts(e, opts));
   if (!d_hwc) return fail(SCV_ERR_INVALID, "d_hwc is NULL");
-  if (out_channel < 0 || out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", out_channel);
-  std::vector<int> ys, xs;
-  chip_grid(H, W, tiling, &ys, &xs);
-  const int nrows = (int)ys.size();
-  if (tile_row_end < 0 || tile_row_end > nrows) tile_row_end = nrows;
-  tile_row_begin = std::max(0, tile_row_begin);
+  MosaicGeom g;
+  SCV_TRY(mosaic_geom(e, H, W, tiling, opts, &g));
   reset_timing(e);
   e->times_pending = true;
-  if (tile_row_begin >= tile_row_end || xs.empty()) return SCV_OK;  // empty chip list: nothing predicted
-  const int half = tiling->buff / 2, side = tiling->kernel + tiling->buff;
-  const int n = (tile_row_end - tile_row_begin) * (int)xs.size();
-  std::vector<int2> org(2 * (size_t)n);
-  int force_scalar = 0;
-  {
-    int k = 0;
-    for (int r = tile_row_begin; r < tile_row_end; ++r)
-      for (int x : xs) {
-        org[k] = make_int2(x - half, ys[r] - half);
-        org[n + k] = make_int2(x, ys[r]);
-        if (x & 3) force_scalar = 1;
-        ++k;
-      }
-  }
-  if (ys[tile_row_begin] - half < src_row0) return fail(SCV_ERR_INVALID, "src_row0=%d is below the first needed mosaic row %d", src_row0, ys[tile_row_begin] - half);
-  if (ys[tile_row_begin] < dst_row0) return fail(SCV_ERR_INVALID, "dst_row0=%d is below the first written row %d", dst_row0, ys[tile_row_begin]);
+  if (g.n() == 0) return SCV_OK;  // empty chip list: nothing predicted
+  if (g.ys[g.r_first] - g.half < src_row0) return fail(SCV_ERR_INVALID, "src_row0=%d is below the first needed mosaic row %d", src_row0, g.ys[g.r_first] - g.half);
+  if (g.ys[g.r_first] < dst_row0) return fail(SCV_ERR_INVALID, "dst_row0=%d is below the first written row %d", dst_row0, g.ys[g.r_first]);
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, org.size() * sizeof(int2)));
-  CUDA_TRY(cudaMemcpyAsync(e->d_origins, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaStreamSynchronize(s));  // org is a stack-lifetime host vector
+  int force_scalar = 0;
+  SCV_TRY(upload_origins(e, g, H, W, s, &force_scalar));
 
   TileJob job{};
+  fill_mosaic_job(&job, g, dtype, W, C, norm, opts, force_scalar, e->d_origins);
   job.d_src = d_hwc;
-  const int last_row = ys[tile_row_end - 1] - half + side;  // exclusive
+  const int last_row = g.ys[g.r_last] - g.half + g.side;  // exclusive
   job.src_bytes = (size_t)(last_row - src_row0) * W * C * dtype_bytes(dtype);
-  job.dtype = dtype;
-  job.src_W = W;
-  job.C = C;
   job.src_row0 = src_row0;
-  job.side = side;
-  job.d_src_origins = e->d_origins;
-  job.norm = norm;
-  job.d_dst_origins = e->d_origins + n;
-  job.kernel = tiling->kernel;
-  job.crop = half;
-  job.out_W = W;
   job.dst_row0 = dst_row0;
-  job.out_channel = out_channel;
-  job.force_scalar = force_scalar;
   job.d_prob = d_prob;
   job.d_mask = d_mask;
   std::vector<std::vector<int>> supers;
-  super_batches(n, e->arch.cfg.max_batch, e->opt_super_tiles, &supers);
+  super_batches(g.n(), e->arch.cfg.max_batch, e->opt_super_tiles, &supers);
   int t0 = 0;
   for (auto& sizes : supers) {
     SCV_TRY(run_super(e, job, t0, sizes, s));
@@ -1390,128 +1542,260 @@ int scv_predict_mosaic_device(scv_engine* e, const void* d_hwc, int dtype, int H
   return SCV_OK;
 }
 
-int scv_predict_mosaic(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
-                       const scv_norm* norm, int tile_row_begin, int tile_row_end, int out_channel, float* out_prob,
-                       uint8_t* out_mask) {
-  SCV_TRY(precheck(e, dtype, C));
-  SCV_TRY(check_tiling(e, tiling));
-  if (!hwc || !out_prob) return fail(SCV_ERR_INVALID, "NULL buffer");
-  if (out_channel < 0 || out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", out_channel);
-  std::vector<int> ys, xs;
-  chip_grid(H, W, tiling, &ys, &xs);
-  const int nrows = (int)ys.size(), ncols = (int)xs.size();
-  if (tile_row_end < 0 || tile_row_end > nrows) tile_row_end = nrows;
-  tile_row_begin = std::max(0, tile_row_begin);
+static void rows_to_opts(const scv_engine* e, int H, int W, const scv_tiling* t, int row_begin, int row_end, int out_channel,
+                         scv_mosaic_opts* o) {
+  memset(o, 0, sizeof *o);
+  o->out_channel = out_channel;
+  if (!t || t->kernel <= 0) return;
+  const int side = t->buff + t->kernel, half = t->buff / 2;
+  int nrows = 0, ncols = 0;
+  for (int y = half; y < H - side; y += t->kernel) ++nrows;
+  for (int x = half; x < W - side; x += t->kernel) ++ncols;
+  if (row_end < 0 || row_end > nrows) row_end = nrows;
+  row_begin = std::max(0, row_begin);
+  o->tile_begin = row_begin * ncols;
+  o->tile_end = row_end * ncols;
+  if (o->tile_end <= o->tile_begin) o->tile_begin = o->tile_end = nrows * ncols + 1;  // empty range (tile_end <= 0 would mean "all")
+  (void)e;
+}
+
+int scv_predict_mosaic_device(scv_engine* e, const void* d_hwc, int dtype, int H, int W, int C, int src_row0,
+                              const scv_tiling* tiling, const scv_norm* norm, int tile_row_begin, int tile_row_end,
+                              int out_channel, float* d_prob, uint8_t* d_mask, int dst_row0, void* stream) {
+  scv_mosaic_opts o;
+  rows_to_opts(e, H, W, tiling, tile_row_begin, tile_row_end, out_channel, &o);
+  return scv_predict_mosaic_device_ex(e, d_hwc, dtype, H, W, C, src_row0, tiling, norm, &o, d_prob, d_mask, dst_row0, stream);
+}
+
+// Page-locks [p, p+bytes) for the duration of a scene unless it already is (cudaHostAlloc / registered memory):
+// pageable buffers would turn every cudaMemcpyAsync below into a synchronous staged copy.
+static void maybe_register(scv_engine* e, scv_engine::Slot& sl, const void* p, size_t bytes) {
+  if (!e->opt_host_register || !p || bytes == 0) return;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  if (at.type != cudaMemoryTypeUnregistered) return;
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(4095);
+  const uintptr_t hi = (reinterpret_cast<uintptr_t>(p) + bytes + 4095) & ~uintptr_t(4095);
+  if (cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterPortable) == cudaSuccess)
+    sl.registered.push_back(reinterpret_cast<void*>(lo));
+  else
+    cudaGetLastError();  // not fatal: the copies fall back to staged transfers
+}
+
+// Blocks until the scene that last used `sl` is complete in host memory, then releases its host registrations.
+static int slot_wait(scv_engine* e, scv_engine::Slot& sl) {
+  if (!sl.busy) return SCV_OK;
+  cudaError_t err = cudaEventSynchronize(sl.d2h_done);
+  cudaError_t err2 = cudaEventSynchronize(sl.compute_done);
+  sl.busy = false;
+  slot_release_host(sl);
+  CUDA_TRY(err);
+  CUDA_TRY(err2);
+  return check_device_err(e);
+}
+
+static cudaEvent_t slot_event(std::vector<cudaEvent_t>& pool, size_t i) {
+  while (pool.size() <= i) {
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    pool.push_back(ev);
+  }
+  return pool[i];
+}
+
+// Enqueues one scene on slot `sl` (H2D per tile row on the copy stream, K1 / network / K4 per super-batch on the
+// compute stream, D2H of every completed tile row on the third stream) and returns without waiting.
+static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* hwc, int dtype, int H, int W, int C,
+                              const scv_tiling* tiling, const scv_norm* norm, const scv_mosaic_opts* opts,
+                              void* out_prob, uint8_t* out_mask, bool may_register) {
+  MosaicGeom g;
+  SCV_TRY(mosaic_geom(e, H, W, tiling, opts, &g));
   reset_timing(e);
   e->times_pending = true;
-  if (tile_row_begin >= tile_row_end || ncols == 0) return SCV_OK;
-  const int half = tiling->buff / 2, side = tiling->kernel + tiling->buff, K = tiling->kernel;
-  const int es = dtype_bytes(dtype);
+  if (g.n() == 0) return SCV_OK;
+  const int es = dtype_bytes(dtype), K = g.K;
+  const bool f64 = opts && opts->out_dtype == SCV_F64, acc = opts && opts->accumulate;
+  const size_t osz = f64 ? 8 : 4;
   const size_t row_bytes = (size_t)W * C * es;
-  const int src_row0 = ys[tile_row_begin] - half;
-  const int src_row1 = ys[tile_row_end - 1] - half + side;
-  const int dst_row0 = ys[tile_row_begin];
-  const int dst_rows = (tile_row_end - tile_row_begin) * K;
-  SCV_TRY(ensure(&e->d_scene, &e->scene_bytes, (size_t)(src_row1 - src_row0) * row_bytes));
-  SCV_TRY(ensure((void**)&e->d_prob, &e->prob_bytes, (size_t)dst_rows * W * sizeof(float)));
-  if (out_mask) SCV_TRY(ensure((void**)&e->d_mask, &e->mask_bytes, (size_t)dst_rows * W));
-
-  const int n = (tile_row_end - tile_row_begin) * ncols;
-  std::vector<int2> org(2 * (size_t)n);
-  int force_scalar = 0;
-  {
-    int k = 0;
-    for (int r = tile_row_begin; r < tile_row_end; ++r)
-      for (int x : xs) {
-        org[k] = make_int2(x - half, ys[r] - half);
-        org[n + k] = make_int2(x, ys[r]);
-        if (x & 3) force_scalar = 1;
-        ++k;
-      }
+  const int src_row0 = g.ys[g.r_first] - g.half;
+  const int src_row1 = g.ys[g.r_last] - g.half + g.side;
+  const int dst_row0 = g.ys[g.r_first];
+  const int dst_rows = (g.r_last - g.r_first + 1) * K;
+  SCV_TRY(ensure(&sl.d_scene, &sl.scene_bytes, (size_t)(src_row1 - src_row0) * row_bytes));
+  SCV_TRY(ensure(&sl.d_prob, &sl.prob_bytes, (size_t)dst_rows * W * osz));
+  if (out_mask) SCV_TRY(ensure((void**)&sl.d_mask, &sl.mask_bytes, (size_t)dst_rows * W));
+  if (may_register) {
+    maybe_register(e, sl, (const uint8_t*)hwc + (size_t)src_row0 * row_bytes, (size_t)(src_row1 - src_row0) * row_bytes);
+    maybe_register(e, sl, (uint8_t*)out_prob + (size_t)dst_row0 * W * osz, (size_t)dst_rows * W * osz);
+    if (out_mask) maybe_register(e, sl, out_mask + (size_t)dst_row0 * W, (size_t)dst_rows * W);
   }
-  SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, org.size() * sizeof(int2)));
-  CUDA_TRY(cudaMemcpyAsync(e->d_origins, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+  int force_scalar = 0;
+  SCV_TRY(upload_origins(e, g, H, W, e->stream, &force_scalar));
 
-  // H2D: one chunk per tile row (the K new mosaic rows it needs; the first also brings the top buffer),
-  // all enqueued up front on the copy stream so PCIe runs back to back while compute starts on chunk 0.
-  const int ntr = tile_row_end - tile_row_begin;
-  std::vector<cudaEvent_t> up_ev(ntr), done_ev;
+  // From here on work is in flight: every failure goes through `fail_rc` so the streams are drained before
+  // the caller gets its buffers back.
+  int rc = SCV_OK;
+  cudaError_t ce = cudaSuccess;
+#define HOST_TRY(expr)                                                                                        \
+  do {                                                                                                        \
+    if (rc == SCV_OK && (ce = (expr)) != cudaSuccess)                                                         \
+      rc = fail(SCV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(ce), __FILE__, __LINE__);   \
+  } while (0)
+  auto col_x0 = [&](int c) { return g.xs[c] - g.half; };
+  auto col_x1 = [&](int c) { return g.xs[c] - g.half + g.side; };
+
+  // H2D: one chunk per tile row = the mosaic rows it adds to what the rows above already brought (the first
+  // chunk also carries the top buffer); a chunk's rows that only this tile row reads are narrowed to its chip
+  // columns, the rows it shares with the next tile row to the union of both.  All chunks are enqueued up front
+  // on the copy stream so PCIe runs back to back while compute starts on chunk 0.
+  const int ntr = g.r_last - g.r_first + 1;
   int uploaded = src_row0;
-  for (int r = 0; r < ntr; ++r) {
-    const int need = ys[tile_row_begin + r] - half + side;  // exclusive
-    const uint8_t* hsrc = (const uint8_t*)hwc + (size_t)uploaded * row_bytes;
-    uint8_t* ddst = (uint8_t*)e->d_scene + (size_t)(uploaded - src_row0) * row_bytes;
-    CUDA_TRY(cudaMemcpyAsync(ddst, hsrc, (size_t)(need - uploaded) * row_bytes, cudaMemcpyHostToDevice, e->h2d));
+  for (int r = g.r_first; r <= g.r_last && rc == SCV_OK; ++r) {
+    const int need = g.ys[r] - g.half + g.side;  // exclusive
+    const int share = r < g.r_last ? std::max(uploaded, g.ys[r + 1] - g.half) : need;  // rows >= share are also read by r+1
+    auto copy_rows = [&](int y0, int y1, int xa, int xb) {
+      if (y1 <= y0 || xb <= xa) return;
+      const size_t off = (size_t)xa * C * es;
+      HOST_TRY(cudaMemcpy2DAsync((uint8_t*)sl.d_scene + (size_t)(y0 - src_row0) * row_bytes + off, row_bytes,
+                                 (const uint8_t*)hwc + (size_t)y0 * row_bytes + off, row_bytes, (size_t)(xb - xa) * C * es,
+                                 y1 - y0, cudaMemcpyHostToDevice, e->h2d));
+    };
+    copy_rows(uploaded, share, col_x0(g.c0(r)), col_x1(g.c1(r) - 1));
+    if (r < g.r_last)
+      copy_rows(share, need, col_x0(std::min(g.c0(r), g.c0(r + 1))), col_x1(std::max(g.c1(r), g.c1(r + 1)) - 1));
     uploaded = need;
-    CUDA_TRY(cudaEventCreateWithFlags(&up_ev[r], cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(up_ev[r], e->h2d));
+    if (acc) {  // the rows of the caller's raster this tile row accumulates into
+      const size_t xo = (size_t)g.xs[g.c0(r)], wbytes = (size_t)(g.c1(r) - g.c0(r)) * K * osz;
+      HOST_TRY(cudaMemcpy2DAsync((uint8_t*)sl.d_prob + ((size_t)(g.ys[r] - dst_row0) * W + xo) * osz, (size_t)W * osz,
+                                 (const uint8_t*)out_prob + ((size_t)g.ys[r] * W + xo) * osz, (size_t)W * osz, wbytes, K,
+                                 cudaMemcpyHostToDevice, e->h2d));
+    }
+    cudaEvent_t ev = slot_event(sl.up_ev, r - g.r_first);
+    if (!ev) rc = fail(SCV_ERR_CUDA, "cudaEventCreate failed");
+    else HOST_TRY(cudaEventRecord(ev, e->h2d));
   }
 
   TileJob job{};
-  job.d_src = e->d_scene;
+  fill_mosaic_job(&job, g, dtype, W, C, norm, opts, force_scalar, e->d_origins);
+  job.d_src = sl.d_scene;
   job.src_bytes = (size_t)(src_row1 - src_row0) * row_bytes;
-  job.dtype = dtype;
-  job.src_W = W;
-  job.C = C;
   job.src_row0 = src_row0;
-  job.side = side;
-  job.d_src_origins = e->d_origins;
-  job.norm = norm;
-  job.d_dst_origins = e->d_origins + n;
-  job.kernel = K;
-  job.crop = half;
-  job.out_W = W;
   job.dst_row0 = dst_row0;
-  job.out_channel = out_channel;
-  job.force_scalar = force_scalar;
-  job.d_prob = e->d_prob;
-  job.d_mask = out_mask ? e->d_mask : nullptr;
+  job.d_prob = sl.d_prob;
+  job.d_mask = out_mask ? sl.d_mask : nullptr;
 
-  // host buffers: smaller super-batches than the device-resident path, so that compute starts after a few tile
-  // rows of H2D and the D2H tail after the last K4 stays short
+  // Super-batches: smaller than on the device-resident path so that compute starts after the first tile row(s)
+  // of H2D and the D2H tail after the last K4 stays short.
   std::vector<std::vector<int>> supers;
   const int host_super = e->opt_host_super_tiles > 0 ? e->opt_host_super_tiles : e->arch.cfg.max_batch;
-  super_batches(n, e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &supers);
-  int t0 = 0, rows_downloaded = 0, rows_waited = 0;
-  int rc = SCV_OK;
-  const size_t core_w = (size_t)ncols * K;
+  super_batches(g.n(), e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &supers);
+  int t0 = 0, rows_downloaded = 0, rows_waited = 0, n_row_ev = 0;
   for (auto& sizes : supers) {
+    if (rc != SCV_OK) break;
     int nsup = 0;
     for (int nb : sizes) nsup += nb;
-    const int last_tile_row = (t0 + nsup - 1) / ncols;  // relative tile row this super-batch reaches
-    for (; rows_waited <= last_tile_row; ++rows_waited) cudaStreamWaitEvent(e->stream, up_ev[rows_waited], 0);
+    const int last_tile_row = (g.tb + t0 + nsup - 1) / g.ncols - g.r_first;  // relative tile row this super-batch reaches
+    for (; rows_waited <= last_tile_row && rc == SCV_OK; ++rows_waited)
+      HOST_TRY(cudaStreamWaitEvent(e->stream, sl.up_ev[rows_waited], 0));
+    if (rc != SCV_OK) break;
     if ((rc = run_super(e, job, t0, sizes, e->stream)) != SCV_OK) break;
     t0 += nsup;
-    // D2H of the tile rows completed so far (cores only: columns [xs[0], xs[0]+ncols*K))
-    const int complete = t0 / ncols;
+    // D2H of the tile rows completed so far (cores only)
+    const int complete = (g.tb + t0 == g.te) ? ntr : (g.tb + t0) / g.ncols - g.r_first;
     if (complete > rows_downloaded) {
-      cudaEvent_t ev;
-      cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-      cudaEventRecord(ev, e->stream);
-      cudaStreamWaitEvent(e->d2h, ev, 0);
-      done_ev.push_back(ev);
-      const int r0 = rows_downloaded * K, nr = (complete - rows_downloaded) * K;
-      const size_t doff = (size_t)r0 * W + xs[0];
-      const size_t hoff = (size_t)(dst_row0 + r0) * W + xs[0];
-      cudaMemcpy2DAsync(out_prob + hoff, (size_t)W * 4, e->d_prob + doff, (size_t)W * 4, core_w * 4, nr,
-                        cudaMemcpyDeviceToHost, e->d2h);
-      if (out_mask)
-        cudaMemcpy2DAsync(out_mask + hoff, (size_t)W, e->d_mask + doff, (size_t)W, core_w, nr, cudaMemcpyDeviceToHost,
-                          e->d2h);
+      cudaEvent_t ev = slot_event(sl.row_ev, n_row_ev++);
+      if (!ev) {
+        rc = fail(SCV_ERR_CUDA, "cudaEventCreate failed");
+        break;
+      }
+      HOST_TRY(cudaEventRecord(ev, e->stream));
+      HOST_TRY(cudaStreamWaitEvent(e->d2h, ev, 0));
+      for (int rr = rows_downloaded; rr < complete && rc == SCV_OK; ++rr) {
+        const int r = g.r_first + rr;
+        const size_t xo = (size_t)g.xs[g.c0(r)], wpx = (size_t)(g.c1(r) - g.c0(r)) * K;
+        const size_t doff = (size_t)(g.ys[r] - dst_row0) * W + xo, hoff = (size_t)g.ys[r] * W + xo;
+        HOST_TRY(cudaMemcpy2DAsync((uint8_t*)out_prob + hoff * osz, (size_t)W * osz, (uint8_t*)sl.d_prob + doff * osz,
+                                   (size_t)W * osz, wpx * osz, K, cudaMemcpyDeviceToHost, e->d2h));
+        if (out_mask)
+          HOST_TRY(cudaMemcpy2DAsync(out_mask + hoff, (size_t)W, sl.d_mask + doff, (size_t)W, wpx, K, cudaMemcpyDeviceToHost,
+                                     e->d2h));
+      }
       rows_downloaded = complete;
     }
   }
-  cudaError_t e1 = cudaStreamSynchronize(e->stream);
-  cudaError_t e2 = cudaStreamSynchronize(e->d2h);
-  cudaError_t e3 = cudaStreamSynchronize(e->h2d);
-  for (auto ev : up_ev) cudaEventDestroy(ev);
-  for (auto ev : done_ev) cudaEventDestroy(ev);
-  if (rc != SCV_OK) return rc;
-  CUDA_TRY(e1);
-  CUDA_TRY(e2);
-  CUDA_TRY(e3);
-  SCV_TRY(check_device_err(e));
+#undef HOST_TRY
+  sl.busy = true;
+  cudaEventRecord(sl.compute_done, e->stream);
+  cudaEventRecord(sl.d2h_done, e->d2h);
+  if (rc != SCV_OK) {  // drain everything that was enqueued against the caller's buffers before reporting
+    const std::string msg = g_err;
+    cudaStreamSynchronize(e->h2d);
+    cudaStreamSynchronize(e->stream);
+    cudaStreamSynchronize(e->d2h);
+    sl.busy = false;
+    slot_release_host(sl);
+    g_err = msg;
+  }
+  return rc;
+}
+
+static int host_args_check(scv_engine* e, const void* hwc, int dtype, int C, const scv_mosaic_opts* opts, void* out_prob) {
+  SCV_TRY(precheck(e, dtype, C));
+  SCV_TRY(check_opts(e, opts));
+  if (!hwc || !out_prob) return fail(SCV_ERR_INVALID, "NULL buffer");
   return SCV_OK;
+}
+
+int scv_stream_submit(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
+                      const scv_norm* norm, const scv_mosaic_opts* opts, void* out_prob, uint8_t* out_mask, int* ticket) {
+  DeviceGuard guard;
+  SCV_TRY(host_args_check(e, hwc, dtype, C, opts, out_prob));
+  const int t = e->next_ticket;
+  scv_engine::Slot& sl = e->slots[t & 1];
+  SCV_TRY(slot_wait(e, sl));  // at most two scenes in flight
+  SCV_TRY(submit_host_mosaic(e, sl, hwc, dtype, H, W, C, tiling, norm, opts, out_prob, out_mask, false));
+  sl.ticket = t;
+  e->next_ticket = t + 1;
+  if (ticket) *ticket = t;
+  return SCV_OK;
+}
+
+int scv_stream_wait(scv_engine* e, int ticket) {
+  if (!e) return fail(SCV_ERR_INVALID, "engine is NULL");
+  DeviceGuard guard;
+  CUDA_TRY(cudaSetDevice(e->device));
+  int rc = SCV_OK;
+  // scenes complete in submission order: waiting for ticket t means waiting for every busy slot up to t
+  for (int k = 0; k < 2; ++k) {
+    scv_engine::Slot& sl = e->slots[(e->next_ticket + k) & 1];  // older slot first
+    if (sl.busy && (ticket < 0 || sl.ticket <= ticket)) {
+      const int r = slot_wait(e, sl);
+      if (rc == SCV_OK) rc = r;
+    }
+  }
+  return rc;
+}
+
+int scv_predict_mosaic_ex(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
+                          const scv_norm* norm, const scv_mosaic_opts* opts, void* out_prob, uint8_t* out_mask) {
+  DeviceGuard guard;
+  SCV_TRY(host_args_check(e, hwc, dtype, C, opts, out_prob));
+  for (auto& sl : e->slots) SCV_TRY(slot_wait(e, sl));  // a synchronous call does not overtake streamed scenes
+  scv_engine::Slot& sl = e->slots[0];
+  SCV_TRY(submit_host_mosaic(e, sl, hwc, dtype, H, W, C, tiling, norm, opts, out_prob, out_mask, true));
+  sl.ticket = -1;
+  return slot_wait(e, sl);
+}
+
+int scv_predict_mosaic(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
+                       const scv_norm* norm, int tile_row_begin, int tile_row_end, int out_channel, float* out_prob,
+                       uint8_t* out_mask) {
+  scv_mosaic_opts o;
+  rows_to_opts(e, H, W, tiling, tile_row_begin, tile_row_end, out_channel, &o);
+  return scv_predict_mosaic_ex(e, hwc, dtype, H, W, C, tiling, norm, &o, out_prob, out_mask);
 }
 
 // shared by predict_tiles / predict_patches: upload stacked patches batch by batch
@@ -1526,10 +1810,11 @@ static int run_stacked(scv_engine* e, const void* nhwc, int dtype, int N, int H,
   balanced_batches(N, e->arch.cfg.max_batch, &sizes);
   const int maxb = sizes.empty() ? 0 : sizes[0];
   SCV_TRY(ensure(&e->d_stage, &e->stage_bytes, (size_t)maxb * tile_bytes));
-  std::vector<int2> org((size_t)maxb);
-  for (int i = 0; i < maxb; ++i) org[i] = make_int2(0, i * H);
   // origins layout: [maxb stacked-source origins][N destination origins] (the latter filled by the caller)
-  CUDA_TRY(cudaMemcpyAsync(e->d_origins, org.data(), org.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+  e->origins_valid = false;
+  e->h_origins.resize((size_t)maxb);
+  for (int i = 0; i < maxb; ++i) e->h_origins[i] = make_int2(0, i * H);
+  CUDA_TRY(cudaMemcpyAsync(e->d_origins, e->h_origins.data(), e->h_origins.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
   job.d_src = e->d_stage;
   job.dtype = dtype;
   job.src_W = W;
@@ -1542,7 +1827,7 @@ static int run_stacked(scv_engine* e, const void* nhwc, int dtype, int N, int H,
     CUDA_TRY(cudaMemcpyAsync(e->d_stage, (const uint8_t*)nhwc + (size_t)t0 * tile_bytes, (size_t)nb * tile_bytes,
                              cudaMemcpyHostToDevice, e->stream));
     job.src_bytes = (size_t)nb * tile_bytes;
-    // run_batch offsets origin arrays and per-tile outputs by t0: compensate for the per-batch staging
+    // run_super offsets origin arrays and per-tile outputs by t0: compensate for the per-batch staging
     TileJob bj = job;
     bj.d_src_origins = e->d_origins - t0;
     SCV_TRY(run_super(e, bj, t0, std::vector<int>{nb}, e->stream));
@@ -1561,9 +1846,11 @@ static int run_stacked(scv_engine* e, const void* nhwc, int dtype, int N, int H,
 
 int scv_predict_tiles(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C, const scv_norm* norm,
                       float* probs, int32_t* classes) {
+  DeviceGuard guard;
   SCV_TRY(precheck(e, dtype, C));
   if (!nhwc) return fail(SCV_ERR_INVALID, "nhwc is NULL");
   if (N < 0) return fail(SCV_ERR_INVALID, "N < 0");
+  for (auto& sl : e->slots) SCV_TRY(slot_wait(e, sl));
   reset_timing(e);
   e->times_pending = true;
   if (N == 0) return SCV_OK;
@@ -1579,42 +1866,59 @@ int scv_predict_tiles(scv_engine* e, const void* nhwc, int dtype, int N, int H, 
   return run_stacked(e, nhwc, dtype, N, H, W, C, norm, job, probs, classes);
 }
 
-int scv_predict_patches(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C,
-                        const scv_tiling* tiling, const scv_norm* norm, int cols, int out_channel, float* out_prob,
-                        uint8_t* out_mask) {
+int scv_predict_patches_ex(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C, const scv_crop* crop,
+                           const scv_norm* norm, int cols, int out_channel, float* out_prob, uint8_t* out_mask) {
+  DeviceGuard guard;
   SCV_TRY(precheck(e, dtype, C));
-  SCV_TRY(check_tiling(e, tiling));
-  if (!nhwc || !out_prob) return fail(SCV_ERR_INVALID, "NULL buffer");
-  const int side = tiling->kernel + tiling->buff, K = tiling->kernel;
-  if (H != side || W != side) return fail(SCV_ERR_INVALID, "patches are %dx%d but kernel+buff=%d", H, W, side);
+  if (!nhwc || !out_prob || !crop) return fail(SCV_ERR_INVALID, "NULL buffer");
+  if (H % (1 << e->arch.cfg.nlevels) || W % (1 << e->arch.cfg.nlevels))
+    return fail(SCV_ERR_INVALID, "patch %dx%d: H and W must be multiples of %d", H, W, 1 << e->arch.cfg.nlevels);
+  if (crop->h <= 0 || crop->w <= 0 || crop->y0 < 0 || crop->x0 < 0 || crop->y0 + crop->h > H || crop->x0 + crop->w > W)
+    return fail(SCV_ERR_INVALID, "crop window [%d:%d, %d:%d] leaves the %dx%d patch", crop->y0, crop->y0 + crop->h, crop->x0,
+                crop->x0 + crop->w, H, W);
   if (cols <= 0 || N % cols) return fail(SCV_ERR_INVALID, "N=%d patches do not fill rows of %d", N, cols);
   if (out_channel < 0 || out_channel >= e->arch.cfg.nclasses) return fail(SCV_ERR_INVALID, "out_channel %d out of range", out_channel);
+  for (auto& sl : e->slots) SCV_TRY(slot_wait(e, sl));
   reset_timing(e);
   e->times_pending = true;
   if (N == 0) return SCV_OK;
   const int rows = N / cols;
-  const size_t out_px = (size_t)rows * K * cols * K;
+  const size_t out_px = (size_t)rows * crop->h * cols * crop->w;
   SCV_TRY(ensure((void**)&e->d_prob, &e->prob_bytes, out_px * 4));
   if (out_mask) SCV_TRY(ensure((void**)&e->d_mask, &e->mask_bytes, out_px));
   const int maxb = e->arch.cfg.max_batch;
   SCV_TRY(ensure((void**)&e->d_origins, &e->origins_cap, (size_t)(maxb + N + 1) * sizeof(int2)));
   std::vector<int2> dst((size_t)N);
-  for (int i = 0; i < N; ++i) dst[i] = make_int2((i % cols) * K, (i / cols) * K);
-  CUDA_TRY(cudaMemcpy(e->d_origins + maxb, dst.data(), dst.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  for (int i = 0; i < N; ++i) dst[i] = make_int2((i % cols) * crop->w, (i / cols) * crop->h);
+  // on the compute stream, like every kernel that reads it (a pageable source is staged before the call returns)
+  CUDA_TRY(cudaMemcpyAsync(e->d_origins + maxb, dst.data(), dst.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
   TileJob job{};
   job.d_dst_origins = e->d_origins + maxb;
-  job.kernel = K;
-  job.crop = tiling->buff / 2;
-  job.out_W = cols * K;
+  job.kernel_h = crop->h;
+  job.kernel_w = crop->w;
+  job.crop_y = crop->y0;
+  job.crop_x = crop->x0;
+  job.out_W = cols * crop->w;
   job.dst_row0 = 0;
   job.out_channel = out_channel;
-  job.force_scalar = (K & 3) ? 1 : 0;
+  job.force_scalar = (crop->w & 3) ? 3 : ((crop->w & 7) ? 2 : 0);
   job.d_prob = e->d_prob;
   job.d_mask = out_mask ? e->d_mask : nullptr;
   SCV_TRY(run_stacked(e, nhwc, dtype, N, H, W, C, norm, job, nullptr, nullptr));
   CUDA_TRY(cudaMemcpy(out_prob, e->d_prob, out_px * 4, cudaMemcpyDeviceToHost));
   if (out_mask) CUDA_TRY(cudaMemcpy(out_mask, e->d_mask, out_px, cudaMemcpyDeviceToHost));
   return SCV_OK;
+}
+
+int scv_predict_patches(scv_engine* e, const void* nhwc, int dtype, int N, int H, int W, int C,
+                        const scv_tiling* tiling, const scv_norm* norm, int cols, int out_channel, float* out_prob,
+                        uint8_t* out_mask) {
+  if (!e) return fail(SCV_ERR_INVALID, "engine is NULL");
+  SCV_TRY(check_tiling(e, tiling));
+  const int side = tiling->kernel + tiling->buff;
+  if (H != side || W != side) return fail(SCV_ERR_INVALID, "patches are %dx%d but kernel+buff=%d", H, W, side);
+  const scv_crop crop = {tiling->buff / 2, tiling->buff / 2, tiling->kernel, tiling->kernel};
+  return scv_predict_patches_ex(e, nhwc, dtype, N, H, W, C, &crop, norm, cols, out_channel, out_prob, out_mask);
 }
 
 // ------------------------------------------------------------------ debug entries

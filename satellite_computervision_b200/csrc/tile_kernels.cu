@@ -59,6 +59,31 @@ __device__ __forceinline__ float exact_div_for_bf16(float t, float div, float rd
   return q;
 }
 
+// Which (tile, first row) a block works on.  Legacy mapping: blockIdx.y = tile, blockIdx.x = row block.
+// Ordered mapping (regular chip grid, p.order_kernel > 0): blockIdx.y = SOURCE row block m (in units of
+// `rpb` mosaic rows from the first chip's top row), blockIdx.x = slot * tiles_per_row + column; slot s looks at
+// tile row floor(m / kb) - s (kb = kernel / rpb).  Vertically adjacent chips share side - kernel rows: the two
+// blocks that read the same mosaic rows are then only tiles_per_row blocks apart, so the second read hits L2
+// instead of DRAM (ncu, round 1: 2.10 GB read for 1.42 GB of unique mosaic bytes).
+__device__ __forceinline__ bool extract_block_unit(const ExtractParams& p, int rpb, int& tile, int& r0) {
+  if (p.order_kernel <= 0) {
+    tile = blockIdx.y;
+    r0 = blockIdx.x * rpb;
+    return r0 < p.side;
+  }
+  const int kb = p.order_kernel / rpb, sb = p.side / rpb;
+  const int slot = blockIdx.x / p.tiles_per_row, col = blockIdx.x - slot * p.tiles_per_row;
+  const int m = blockIdx.y;
+  const int tr = m / kb - slot;
+  if (tr < 0) return false;
+  const int rb = m - tr * kb;
+  if (rb >= sb) return false;
+  tile = tr * p.tiles_per_row + col - p.order_skip;  // the launch holds chips [order_skip, order_skip + n_tiles) of the grid
+  if (tile < 0 || tile >= p.n_tiles) return false;
+  r0 = rb * rpb;
+  return true;
+}
+
 // K1.  One block = `rows_per_block` rows of one chip.  Stage: the rows' bytes are fetched with 128-bit
 // loads from the 16-byte-aligned span covering them (any element alignment of the chip origin is handled)
 // into shared memory.  Compute: one thread per pixel reads its C bands from shared memory, normalises in
@@ -70,8 +95,8 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
   constexpr int esize = DT == SCV_U8 ? 1 : (DT == SCV_U16 || DT == SCV_I16) ? 2 : (DT == SCV_F32 ? 4 : 8);
   constexpr int NV = CT > 0 ? ((CT + 7) / 8) * 8 : SCV_MAX_BANDS;  // values held per pixel
   const int C = CT > 0 ? CT : p.C;
-  const int tile = blockIdx.y;
-  const int r0 = blockIdx.x * p.rows_per_block;
+  int tile, r0;
+  if (!extract_block_unit(p, p.rows_per_block, tile, r0)) return;
   const int2 org = p.origins[tile];
   const int row_bytes = p.side * C * esize;
   const int sstride = smem_row_stride(row_bytes);
@@ -126,35 +151,72 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
 #pragma unroll
         for (int c = 0; c < NV; ++c)
           if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], st[2 * c]), st[2 * c + 1]);
-      } else if (mode == SCV_NORM_PIXEL_MINMAX) {
-        float mn = v[0], mx = v[0];
+      } else if (mode == SCV_NORM_PIXEL_MINMAX || mode == SCV_NORM_PIXEL_ZSCORE || mode == SCV_NORM_PIXEL_ZSCORE_SD) {
+        // per pixel, independently per channel group (splits=); channels beyond the last group pass through
+        const int ng = p.ngroups > 0 ? p.ngroups : 1;
+        for (int g = 0; g < ng; ++g) {
+          const int b0 = (p.ngroups > 0 && g > 0) ? p.group_end[g - 1] : 0;
+          const int b1 = p.ngroups > 0 ? p.group_end[g] : C;
+          if (mode == SCV_NORM_PIXEL_MINMAX) {
+            float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-        for (int c = 1; c < NV; ++c)
-          if (c < C) {
-            mn = fminf(mn, v[c]);
-            mx = fmaxf(mx, v[c]);
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1) {
+                mn = fminf(mn, v[c]);
+                mx = fmaxf(mx, v[c]);
+              }
+            const float den = __fadd_rn(__fsub_rn(mx, mn), p.div[0]);
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1) v[c] = __fdiv_rn(__fsub_rn(v[c], mn), den);
+          } else if (mode == SCV_NORM_PIXEL_ZSCORE) {
+            const float n = static_cast<float>(b1 - b0);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1) sum = __fadd_rn(sum, v[c]);
+            const float mean = __fdiv_rn(sum, n);
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1) {
+                const float d = __fsub_rn(v[c], mean);
+                ss = __fadd_rn(ss, __fmul_rn(d, d));
+              }
+            const float den = __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, n), p.div[0]));
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1) v[c] = __fdiv_rn(__fsub_rn(v[c], mean), den);
+          } else {
+            // normalize_dataArray: nanmean / nanstd (population) across the bands, (x - mean) / (sd + eps)
+            float sum = 0.f, n = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1 && v[c] == v[c]) {
+                sum = __fadd_rn(sum, v[c]);
+                n += 1.f;
+              }
+            const float mean = __fdiv_rn(sum, n);  // all-NaN pixel: 0/0 = NaN, like np.nanmean
+            float ss = 0.f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1 && v[c] == v[c]) {
+                const float d = __fsub_rn(v[c], mean);
+                ss = __fadd_rn(ss, __fmul_rn(d, d));
+              }
+            const float den = __fadd_rn(__fsqrt_rn(__fdiv_rn(ss, n)), p.div[0]);
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+              if (c >= b0 && c < b1) v[c] = __fdiv_rn(__fsub_rn(v[c], mean), den);
           }
-        const float den = __fadd_rn(__fsub_rn(mx, mn), p.div[0]);
+        }
+      }
+      if (p.valid_y1 > p.valid_y0) {  // outside the valid window: exact zeros AFTER normalisation
+        const int gy = org.y + r0 + rr, gx = org.x + x;
+        if (gy < p.valid_y0 || gy >= p.valid_y1 || gx < p.valid_x0 || gx >= p.valid_x1) {
 #pragma unroll
-        for (int c = 0; c < NV; ++c)
-          if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mn), den);
-      } else if (mode == SCV_NORM_PIXEL_ZSCORE) {
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < NV; ++c)
-          if (c < C) sum = __fadd_rn(sum, v[c]);
-        const float mean = __fdiv_rn(sum, static_cast<float>(C));
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < NV; ++c)
-          if (c < C) {
-            const float d = __fsub_rn(v[c], mean);
-            ss = __fadd_rn(ss, __fmul_rn(d, d));
-          }
-        const float den = __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, static_cast<float>(C)), p.div[0]));
-#pragma unroll
-        for (int c = 0; c < NV; ++c)
-          if (c < C) v[c] = __fdiv_rn(__fsub_rn(v[c], mean), den);
+          for (int c = 0; c < NV; ++c) v[c] = 0.f;
+        }
       }
 
       uint4* o4 = reinterpret_cast<uint4*>(orow + static_cast<size_t>(x) * p.cpad);
@@ -183,8 +245,9 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
 // line is consumed by the same warp within three consecutive instructions (L1 hits).
 template <bool SUB>
 __global__ void __launch_bounds__(256) extract_u16x6_kernel(const ExtractParams p) {
-  const int tile = blockIdx.y;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int tile, r0;
+  if (!extract_block_unit(p, 8, tile, r0)) return;
+  const int row = r0 + (threadIdx.x >> 5);
   if (row >= p.side) return;
   const int lane = threadIdx.x & 31;
   const int2 org = p.origins[tile];
@@ -230,14 +293,16 @@ __global__ void __launch_bounds__(256) extract_u16x6_kernel(const ExtractParams 
     o.y = pack2(q[2], q[3]);
     o.z = pack2(q[4], q[5]);
     o.w = 0u;
-    dst[x] = o;
+    __stcs(dst + x, o);  // streaming: the whole scene's tiles are written before the first conv reads them
   }
 }
 
-// Per-tile per-band statistics for SCV_NORM_TILE_* (one block per tile).
-// Two passes like tf.nn.moments: mean, then mean of squared differences.
+// Per-tile statistics for SCV_NORM_TILE_* (one block per tile): per band (axes=[0,1]) or, for the GLOBAL
+// modes (axes=[0,1,2]), per channel group.  Two passes like tf.nn.moments: mean, then mean of squared
+// differences.  Output: per band (sub, div) so the extract kernel applies (x - sub) / div either way.
 __global__ void __launch_bounds__(256) tile_stats_kernel(const TileStatsParams p) {
   __shared__ float red[2][SCV_MAX_BANDS][8];
+  __shared__ float band[2][SCV_MAX_BANDS];
   __shared__ float s_mean[SCV_MAX_BANDS];
   const int tile = blockIdx.x;
   const int2 org = p.origins[tile];
@@ -245,7 +310,8 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const TileStatsParams p
   const int C = p.C;
   const int npix = p.side * p.side;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool zs = p.mode == SCV_NORM_TILE_ZSCORE;
+  const bool zs = p.mode == SCV_NORM_TILE_ZSCORE || p.mode == SCV_NORM_TILE_GLOBAL_ZSCORE;
+  const bool global = p.mode == SCV_NORM_TILE_GLOBAL_ZSCORE || p.mode == SCV_NORM_TILE_GLOBAL_MINMAX;
 
   float a[SCV_MAX_BANDS], b[SCV_MAX_BANDS];
   for (int pass = 0; pass < (zs ? 2 : 1); ++pass) {
@@ -297,12 +363,48 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const TileStatsParams p
         ra = zs ? ra + red[0][c][w] : fminf(ra, red[0][c][w]);
         rb = zs ? rb + red[1][c][w] : fmaxf(rb, red[1][c][w]);
       }
+      band[0][c] = ra;
+      band[1][c] = rb;
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      const int c = threadIdx.x;
+      float ra = band[0][c], rb = band[1][c];
+      float count = static_cast<float>(npix);
+      bool pass_through = false;
+      if (global) {  // combine the bands of this band's group
+        const int ng = p.ngroups > 0 ? p.ngroups : 1;
+        int b0 = 0, b1 = p.ngroups > 0 ? 0 : C;
+        pass_through = p.ngroups > 0;
+        for (int g = 0; g < ng && p.ngroups > 0; ++g) {
+          const int lo = g > 0 ? p.group_end[g - 1] : 0, hi = p.group_end[g];
+          if (c >= lo && c < hi) {
+            b0 = lo, b1 = hi;
+            pass_through = false;
+          }
+        }
+        if (!pass_through) {
+          ra = band[0][b0];
+          rb = band[1][b0];
+          for (int k = b0 + 1; k < b1; ++k) {
+            ra = zs ? ra + band[0][k] : fminf(ra, band[0][k]);
+            rb = zs ? rb + band[1][k] : fmaxf(rb, band[1][k]);
+          }
+          count *= static_cast<float>(b1 - b0);
+        }
+      } else if (p.ngroups > 0 && c >= p.group_end[p.ngroups - 1]) {
+        pass_through = true;
+      }
       float* st = p.stats + (static_cast<size_t>(tile) * C + c) * 2;
-      if (zs) {
-        if (pass == 0) s_mean[c] = ra / static_cast<float>(npix);
+      if (pass_through) {
+        s_mean[c] = 0.f;
+        st[0] = 0.f;
+        st[1] = 1.f;
+      } else if (zs) {
+        if (pass == 0) s_mean[c] = ra / count;
         else {
           st[0] = s_mean[c];
-          st[1] = sqrtf(ra / static_cast<float>(npix) + p.eps);
+          st[1] = sqrtf(ra / count + p.eps);
         }
       } else {
         st[0] = ra;
@@ -342,49 +444,88 @@ __device__ __forceinline__ void head_eval(const float* z, int ncls, int head, fl
   }
 }
 
-// K4, vector path: sigmoid head (ncls == 1), 4 consecutive core pixels per thread,
-// float4 logit load, float4 probability store, 32-bit mask store.
-__global__ void __launch_bounds__(256) stitch_kernel_vec4(const StitchParams p) {
+template <typename OUT, bool ACC>
+__device__ __forceinline__ void put_prob(void* base, size_t o, float pr) {
+  OUT* q = reinterpret_cast<OUT*>(base) + o;
+  *q = ACC ? static_cast<OUT>(*q + static_cast<OUT>(pr)) : static_cast<OUT>(pr);
+}
+
+// K4, vector path: sigmoid head (ncls == 1), PX (4 or 8) consecutive core pixels per thread: float4 logit
+// loads, float4 / double2 probability stores, one 32- / 64-bit mask store; streaming (evict-first) accesses:
+// nothing here is read again on the device.  OUT = float | double raster, ACC: += instead of = (:154).
+template <int PX, typename OUT, bool ACC>
+__global__ void __launch_bounds__(256) stitch_kernel_vec(const StitchParams p) {
   const int tile = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per_row = p.kernel >> 2;
-  if (q >= per_row * p.kernel) return;
+  const int per_row = p.kernel_w / PX;
+  if (q >= per_row * p.kernel_h) return;
   const int row = q / per_row;
-  const int col = (q - row * per_row) << 2;
+  const int col = (q - row * per_row) * PX;
   const int2 d = p.dst_origins[tile];
-  const float4 z = __ldg(reinterpret_cast<const float4*>(
-      p.logits + (static_cast<size_t>(tile) * p.side + (p.crop + row)) * p.side + p.crop + col));
-  float4 pr;
-  pr.x = 1.f / (1.f + expf(-z.x));
-  pr.y = 1.f / (1.f + expf(-z.y));
-  pr.z = 1.f / (1.f + expf(-z.z));
-  pr.w = 1.f / (1.f + expf(-z.w));
+  const float* zsrc = p.logits + (static_cast<size_t>(tile) * p.side + (p.crop_y + row)) * p.side + p.crop_x + col;
+  float z[PX], pr[PX];
+#pragma unroll
+  for (int k = 0; k < PX / 4; ++k) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(zsrc) + k);
+    z[4 * k] = t.x, z[4 * k + 1] = t.y, z[4 * k + 2] = t.z, z[4 * k + 3] = t.w;
+  }
+#pragma unroll
+  for (int k = 0; k < PX; ++k) pr[k] = 1.f / (1.f + expf(-z[k]));
   const size_t o = static_cast<size_t>(d.y + row - p.dst_row0) * p.out_W + d.x + col;
-  if (p.prob) *reinterpret_cast<float4*>(p.prob + o) = pr;
+  if (p.prob) {
+    if constexpr (sizeof(OUT) == 4) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.prob) + o);
+#pragma unroll
+      for (int k = 0; k < PX / 4; ++k) {
+        float4 v = make_float4(pr[4 * k], pr[4 * k + 1], pr[4 * k + 2], pr[4 * k + 3]);
+        if (ACC) {
+          const float4 t = dst[k];
+          v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+        }
+        __stcs(dst + k, v);
+      }
+    } else {
+      double2* dst = reinterpret_cast<double2*>(reinterpret_cast<double*>(p.prob) + o);
+#pragma unroll
+      for (int k = 0; k < PX / 2; ++k) {
+        double2 v = make_double2(static_cast<double>(pr[2 * k]), static_cast<double>(pr[2 * k + 1]));
+        if (ACC) {
+          const double2 t = dst[k];
+          v.x += t.x, v.y += t.y;
+        }
+        __stcs(dst + k, v);
+      }
+    }
+  }
   if (p.mask) {
-    const uint32_t m = (pr.x > p.threshold ? 1u : 0u) | (pr.y > p.threshold ? 1u << 8 : 0u) |
-                       (pr.z > p.threshold ? 1u << 16 : 0u) | (pr.w > p.threshold ? 1u << 24 : 0u);
-    *reinterpret_cast<uint32_t*>(p.mask + o) = m;
+    uint32_t m[PX / 4];
+#pragma unroll
+    for (int k = 0; k < PX / 4; ++k)
+      m[k] = (pr[4 * k] > p.threshold ? 1u : 0u) | (pr[4 * k + 1] > p.threshold ? 1u << 8 : 0u) |
+             (pr[4 * k + 2] > p.threshold ? 1u << 16 : 0u) | (pr[4 * k + 3] > p.threshold ? 1u << 24 : 0u);
+    if constexpr (PX == 8) __stcs(reinterpret_cast<uint2*>(p.mask + o), make_uint2(m[0], m[1]));
+    else __stcs(reinterpret_cast<uint32_t*>(p.mask + o), m[0]);
   }
 }
 
-// K4, general path: any head / class count / alignment, one pixel per thread.
+// K4, general path: any head / class count / alignment / crop window, one pixel per thread.
+template <typename OUT, bool ACC>
 __global__ void __launch_bounds__(256) stitch_kernel_scalar(const StitchParams p) {
   const int tile = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= p.kernel * p.kernel) return;
-  const int row = q / p.kernel;
-  const int col = q - row * p.kernel;
+  if (q >= p.kernel_h * p.kernel_w) return;
+  const int row = q / p.kernel_w;
+  const int col = q - row * p.kernel_w;
   const int2 d = p.dst_origins[tile];
   const float* z =
-      p.logits + ((static_cast<size_t>(tile) * p.side + (p.crop + row)) * p.side + p.crop + col) * p.ncls;
+      p.logits + ((static_cast<size_t>(tile) * p.side + (p.crop_y + row)) * p.side + p.crop_x + col) * p.ncls;
   float zz[SCV_MAX_CLASSES];
   for (int k = 0; k < p.ncls; ++k) zz[k] = __ldg(z + k);
   float prob = 0.f;
   int cls = 0;
   head_eval(zz, p.ncls, p.head, p.threshold, p.out_channel, prob, cls);
   const size_t o = static_cast<size_t>(d.y + row - p.dst_row0) * p.out_W + d.x + col;
-  if (p.prob) p.prob[o] = prob;
+  if (p.prob) put_prob<OUT, ACC>(p.prob, o, prob);
   if (p.mask) p.mask[o] = static_cast<uint8_t>(cls);
 }
 
@@ -435,18 +576,27 @@ size_t extract_smem_bytes(const ExtractParams& p) {
   return static_cast<size_t>(p.rows_per_block) * ((row_bytes + 16 + 15) & ~15);
 }
 
+// grid of an extract launch (see extract_block_unit)
+static dim3 extract_grid(const ExtractParams& p, int rpb) {
+  if (p.order_kernel <= 0) return dim3((p.side + rpb - 1) / rpb, p.n_tiles);
+  const int kb = p.order_kernel / rpb, sb = p.side / rpb;
+  const int n_tile_rows = (p.order_skip + p.n_tiles + p.tiles_per_row - 1) / p.tiles_per_row;
+  return dim3(((sb + kb - 1) / kb) * p.tiles_per_row, (n_tile_rows - 1) * kb + sb);
+}
+
 template <int DT, int CT>
 static cudaError_t launch_extract_tc(const ExtractParams& p, cudaStream_t s) {
   const size_t smem = extract_smem_bytes(p);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // the attribute is per device (one engine per GPU, several per process)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     cudaError_t e =
         cudaFuncSetAttribute(extract_kernel<DT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  dim3 grid((p.side + p.rows_per_block - 1) / p.rows_per_block, p.n_tiles);
-  extract_kernel<DT, CT><<<grid, 256, smem, s>>>(p);
+  extract_kernel<DT, CT><<<extract_grid(p, p.rows_per_block), 256, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <int DT>
@@ -463,19 +613,26 @@ cudaError_t launch_extract(const ExtractParams& pin, cudaStream_t s) {
   if (pin.n_tiles <= 0) return cudaSuccess;
   ExtractParams p = pin;
   for (int c = 0; c < SCV_MAX_BANDS; ++c) p.rdiv[c] = 1.0f / p.div[c];  // fp32 RN reciprocal (host IEEE division)
-  if (p.dtype == SCV_U16 && p.C == 6 && p.cpad == 8 && p.norm_mode == SCV_NORM_PER_BAND &&
-      (reinterpret_cast<uintptr_t>(p.src) & 3) == 0 && !getenv("SCV_K1_GENERIC")) {
+  // source-row-ordered block mapping needs whole row blocks on both the chip side and the chip pitch
+  const bool fast = p.dtype == SCV_U16 && p.C == 6 && p.cpad == 8 && p.norm_mode == SCV_NORM_PER_BAND &&
+                    p.valid_y1 <= p.valid_y0 && (reinterpret_cast<uintptr_t>(p.src) & 3) == 0 && !getenv("SCV_K1_GENERIC");
+  const int rpb = fast ? 8 : p.rows_per_block;
+  if (p.order_kernel > 0 && (p.tiles_per_row <= 0 || p.order_skip < 0 || p.order_skip >= p.tiles_per_row || p.order_kernel % rpb || p.side % rpb ||
+                             p.order_kernel > p.side || getenv("SCV_K1_UNORDERED")))
+    p.order_kernel = 0;
+  if (fast) {
     bool sane = true, sub = false;
     for (int c = 0; c < 6; ++c) {
       sane = sane && p.div[c] >= 1e-3f && p.div[c] <= 1e9f && fabsf(p.sub[c]) <= 1e9f;  // quotients stay normal and finite
       sub = sub || p.sub[c] != 0.f;
     }
     if (sane) {
-      dim3 grid((p.side + 7) / 8, p.n_tiles);
+      const dim3 grid = extract_grid(p, 8);
       if (sub) extract_u16x6_kernel<true><<<grid, 256, 0, s>>>(p);
       else extract_u16x6_kernel<false><<<grid, 256, 0, s>>>(p);
       return cudaGetLastError();
     }
+    if (p.order_kernel > 0 && (p.order_kernel % p.rows_per_block || p.side % p.rows_per_block)) p.order_kernel = 0;
   }
   switch (p.dtype) {
     case SCV_U8: return launch_extract_t<SCV_U8>(p, s);
@@ -493,20 +650,36 @@ cudaError_t launch_tile_stats(const TileStatsParams& p, int n_tiles, cudaStream_
   return cudaGetLastError();
 }
 
-cudaError_t launch_stitch(const StitchParams& p, int n_tiles, cudaStream_t s) {
-  if (n_tiles <= 0) return cudaSuccess;
-  const bool vec = p.head == SCV_HEAD_SIGMOID && p.ncls == 1 && (p.kernel & 3) == 0 && (p.crop & 3) == 0 &&
-                   (p.side & 3) == 0 && (p.out_W & 3) == 0 &&
-                   (reinterpret_cast<uintptr_t>(p.prob) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.mask) & 3) == 0 &&
-                   (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0;
-  if (vec && !p.force_scalar) {
-    dim3 grid(((p.kernel >> 2) * p.kernel + 255) / 256, n_tiles);
-    stitch_kernel_vec4<<<grid, 256, 0, s>>>(p);
+template <typename OUT, bool ACC>
+static cudaError_t launch_stitch_t(const StitchParams& p, int n_tiles, int px, cudaStream_t s) {
+  if (px == 8) {
+    dim3 grid(((p.kernel_w >> 3) * p.kernel_h + 255) / 256, n_tiles);
+    stitch_kernel_vec<8, OUT, ACC><<<grid, 256, 0, s>>>(p);
+  } else if (px == 4) {
+    dim3 grid(((p.kernel_w >> 2) * p.kernel_h + 255) / 256, n_tiles);
+    stitch_kernel_vec<4, OUT, ACC><<<grid, 256, 0, s>>>(p);
   } else {
-    dim3 grid((p.kernel * p.kernel + 255) / 256, n_tiles);
-    stitch_kernel_scalar<<<grid, 256, 0, s>>>(p);
+    dim3 grid((p.kernel_h * p.kernel_w + 255) / 256, n_tiles);
+    stitch_kernel_scalar<OUT, ACC><<<grid, 256, 0, s>>>(p);
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_stitch(const StitchParams& p, int n_tiles, cudaStream_t s) {
+  if (n_tiles <= 0) return cudaSuccess;
+  // vector path: every address a thread touches must be aligned for its PX pixels.  The caller reports the
+  // destination columns through force_scalar: bit 0 = some x origin is not a multiple of 4, bit 1 = not of 8.
+  const int esz = p.prob_f64 ? 8 : 4;
+  auto aligned = [&](int px) {
+    return p.head == SCV_HEAD_SIGMOID && p.ncls == 1 && p.kernel_w % px == 0 && p.crop_x % 4 == 0 && p.side % 4 == 0 &&
+           p.out_W % px == 0 && (reinterpret_cast<uintptr_t>(p.prob) % (px * esz > 16 ? 16 : px * esz)) == 0 &&
+           (reinterpret_cast<uintptr_t>(p.mask) % px) == 0 && (reinterpret_cast<uintptr_t>(p.logits) & 15) == 0;
+  };
+  int px = 1;
+  if (!(p.force_scalar & 1) && aligned(4)) px = 4;
+  if (px == 4 && !(p.force_scalar & 2) && aligned(8)) px = 8;
+  if (p.prob_f64) return p.accumulate ? launch_stitch_t<double, true>(p, n_tiles, px, s) : launch_stitch_t<double, false>(p, n_tiles, px, s);
+  return p.accumulate ? launch_stitch_t<float, true>(p, n_tiles, px, s) : launch_stitch_t<float, false>(p, n_tiles, px, s);
 }
 
 cudaError_t launch_head_tiles(const HeadTilesParams& p, cudaStream_t s) {

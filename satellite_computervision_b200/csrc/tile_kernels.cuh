@@ -31,6 +31,18 @@ struct ExtractParams {
   float rdiv[SCV_MAX_BANDS];  // filled by launch_extract: RN(1 / div)
   const float* tile_stats;   // SCV_NORM_TILE_*: per tile, per band (sub, div)
   __nv_bfloat16* out;        // n_tiles * side * side * cpad
+  // splits= of the data-derived per-pixel modes: channel groups [group_end[g-1], group_end[g]); channels
+  // >= group_end[ngroups-1] pass through
+  int ngroups;
+  int group_end[SCV_MAX_BANDS];
+  // pixels outside [valid_y0, valid_y1) x [valid_x0, valid_x1) (mosaic coordinates) become exact zeros after
+  // normalisation; valid_y1 <= valid_y0: everything is valid
+  int valid_y0, valid_y1, valid_x0, valid_x1;
+  // > 0: the tiles are a regular row-major grid (tiles_per_row per tile row, origins `order_kernel` rows apart):
+  // blocks are then ordered by SOURCE mosaic row, so the rows two vertically adjacent chips share are read
+  // back to back and the second read hits L2
+  // order_skip: chips missing at the start of the first tile row (a chip RANGE that starts mid-row)
+  int order_kernel, tiles_per_row, order_skip;
 };
 
 struct TileStatsParams {
@@ -38,9 +50,11 @@ struct TileStatsParams {
   int dtype, W, C, src_row0;
   const int2* origins;
   int side;
-  int mode;    // SCV_NORM_TILE_ZSCORE or SCV_NORM_TILE_MINMAX
+  int mode;    // SCV_NORM_TILE_ZSCORE / _MINMAX (per band) or SCV_NORM_TILE_GLOBAL_ZSCORE / _MINMAX (per group)
   float eps;
   float* stats;  // n_tiles * C * 2 -> (sub, div)
+  int ngroups;   // global modes: channel groups; bands beyond the last group get (0, 1)
+  int group_end[SCV_MAX_BANDS];
 };
 
 struct StitchParams {
@@ -48,13 +62,15 @@ struct StitchParams {
   int side, ncls, head;
   float threshold;
   int out_channel;
-  int crop;    // buff / 2
-  int kernel;  // kept core side
+  int crop_y, crop_x;        // first kept row / column of a tile (buff / 2)
+  int kernel_h, kernel_w;    // kept core size
   const int2* dst_origins;  // per tile {.x = x, .y = y} of the core's upper-left in output-raster coordinates
-  int force_scalar;         // set when some dst x is not a multiple of 4 (vector path needs aligned stores)
+  int force_scalar;         // bit 0: some dst x is not a multiple of 4, bit 1: not of 8 (vector paths need aligned stores)
   int dst_row0;             // raster row held at prob[0]
   int out_W;
-  float* prob;    // may be null
+  void* prob;     // float or double raster, may be null
+  int prob_f64;   // prob is double (the reference's float64 template, utils/prediction_tools.py:769)
+  int accumulate; // prob[o] += p (utils/prediction_tools.py:154) instead of prob[o] = p
   uint8_t* mask;  // may be null
 };
 

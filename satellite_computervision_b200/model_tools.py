@@ -221,45 +221,81 @@ class UNetModel:
         return probs
 
     def predict_mosaic(self, arr, buff=128, kernel=256, norm=None, out_channel=0, tile_rows=None, want_mask=True,
-                       out_prob=None, out_mask=None):
+                       out_prob=None, out_mask=None, tile_range=None, accumulate=False, valid=None):
         """generate_chip_indices + predict_chips over a whole (H,W,C) raster on the device
-        (``prediction_tools.py:767-776``).  Returns (prob float32 (H,W), mask uint8 (H,W) or None); pixels
-        outside the kept cores are zero, exactly the footprint the reference leaves unpredicted."""
+        (``prediction_tools.py:767-776``).  Returns (prob (H,W), mask uint8 (H,W) or None); pixels
+        outside the kept cores are left untouched (zero for the rasters allocated here), exactly the footprint
+        the reference leaves unpredicted.
+
+        ``out_prob`` may be a caller-owned float32 or float64 (H,W) raster (the reference's float64 template,
+        ``:769``); ``accumulate=True`` adds into it like ``predict_chips`` (``:154``) instead of assigning.
+        ``tile_rows=(r0, r1)`` / ``tile_range=(t0, t1)`` restrict the call to tile rows / to a chip range of
+        the row-major chip list (multi-GPU sharding).  ``valid=(y0, y1, x0, x1)``: pixels outside this window
+        reach the network as exact zeros after normalisation.  Rasters allocated here are page-locked."""
         arr, norm = self._split_norm(arr, norm)
         a, dt = _lib.as_input(arr)
         if a.ndim != 3:
             raise ValueError(f'expected (H, W, C) mosaic, got shape {a.shape}')
         H, W, Cc = a.shape
         if out_prob is None:
-            out_prob = np.zeros((H, W), dtype=np.float32)
+            out_prob = _lib.pinned_zeros((H, W), np.float32)
+        if out_prob.shape != (H, W) or out_prob.dtype not in (np.float32, np.float64) or not out_prob.flags.c_contiguous:
+            raise ValueError('out_prob must be a C-contiguous float32 or float64 (H, W) array')
         if want_mask and out_mask is None:
-            out_mask = np.zeros((H, W), dtype=np.uint8)
+            out_mask = _lib.pinned_zeros((H, W), np.uint8)
+        if want_mask and (out_mask.shape != (H, W) or out_mask.dtype != np.uint8 or not out_mask.flags.c_contiguous):
+            raise ValueError('out_mask must be a C-contiguous uint8 (H, W) array')
         t = _lib.Tiling(int(kernel), int(buff))
         cn = (norm or NormSpec()).to_c(Cc)
-        r0, r1 = (0, -1) if tile_rows is None else tile_rows
-        _lib.check(self._lib.scv_predict_mosaic(self._ensure_engine(), _lib.ptr(a), dt, H, W, Cc, C.byref(t),
-                                                C.byref(cn), r0, r1, out_channel, _lib.ptr(out_prob),
-                                                _lib.ptr(out_mask) if want_mask else None))
+        o = _lib.MosaicOpts()
+        o.out_channel = int(out_channel)
+        o.out_dtype = _lib.SCV_F64 if out_prob.dtype == np.float64 else _lib.SCV_F32
+        o.accumulate = int(bool(accumulate))
+        if valid is not None:
+            for i, v in enumerate(valid):
+                o.valid[i] = int(v)
+        if tile_range is not None:
+            o.tile_begin, o.tile_end = int(tile_range[0]), int(tile_range[1])
+            if o.tile_end <= o.tile_begin:
+                return out_prob, (out_mask if want_mask else None)
+        elif tile_rows is not None:
+            from .sharding import chip_grid
+            ys, xs = chip_grid(H, W, int(kernel), int(buff))
+            r0, r1 = tile_rows
+            r1 = len(ys) if r1 < 0 else min(r1, len(ys))
+            if r1 <= max(r0, 0) or not xs:
+                return out_prob, (out_mask if want_mask else None)
+            o.tile_begin, o.tile_end = max(r0, 0) * len(xs), r1 * len(xs)
+        _lib.check(self._lib.scv_predict_mosaic_ex(self._ensure_engine(), _lib.ptr(a), dt, H, W, Cc, C.byref(t),
+                                                   C.byref(cn), C.byref(o), _lib.ptr(out_prob),
+                                                   _lib.ptr(out_mask) if want_mask else None))
         return out_prob, (out_mask if want_mask else None)
 
     def predict_patches(self, patches, cols, kernel_shape=(256, 256), kernel_buffer=(128, 128), norm=None,
-                        out_channel=0, want_mask=False):
-        """Patch-list geometry (``prediction_tools.py:245-373, :475-520``): crop every patch's buffer
-        and place patch i at row i//cols, col i%cols.  Returns (prob (rows*k, cols*k) f32, mask|None)."""
+                        out_channel=0, want_mask=False, crop=None):
+        """Patch-list geometry (``prediction_tools.py:245-373, :475-520``): crop every patch and place patch i
+        at row i//cols, col i%cols.  ``crop=(y0, y1, x0, x1)`` is the kept window of a patch; by default the
+        literal window of ``:258-261`` / ``:340-343`` (which mixes the x / y names, so a non-square
+        ``kernel_buffer`` keeps a non-square window -- reproduced as written).  Returns
+        (prob (rows*h, cols*w) f32, mask|None)."""
         patches, norm = self._split_norm(patches, norm)
         a, dt = _lib.as_input(patches)
         N, H, W, Cc = a.shape
-        if kernel_shape[0] != kernel_shape[1] or kernel_buffer[0] != kernel_buffer[1]:
-            raise NotImplementedError('non-square kernels are not supported')
-        k, b = int(kernel_shape[0]), int(kernel_buffer[0])
+        if crop is None:
+            x_buffer, y_buffer = int(kernel_buffer[0] / 2), int(kernel_buffer[1] / 2)
+            crop = (y_buffer, kernel_shape[1] + x_buffer, x_buffer, kernel_shape[0] + y_buffer)
+        y0, y1, x0, x1 = (int(v) for v in crop)
+        cw = _lib.Crop(y0, x0, y1 - y0, x1 - x0)
         rows = N // cols
-        prob = np.empty((rows * k, cols * k), dtype=np.float32)
-        mask = np.empty((rows * k, cols * k), dtype=np.uint8) if want_mask else None
-        t = _lib.Tiling(k, b)
+        if N % cols:  # the reference's append loop drops a trailing partial row (:269-291)
+            a = a[:rows * cols]
+            N = rows * cols
+        prob = np.empty((rows * cw.h, cols * cw.w), dtype=np.float32)
+        mask = np.empty((rows * cw.h, cols * cw.w), dtype=np.uint8) if want_mask else None
         cn = (norm or NormSpec()).to_c(Cc)
-        _lib.check(self._lib.scv_predict_patches(self._ensure_engine(), _lib.ptr(a), dt, N, H, W, Cc, C.byref(t),
-                                                 C.byref(cn), int(cols), out_channel, _lib.ptr(prob),
-                                                 _lib.ptr(mask)))
+        _lib.check(self._lib.scv_predict_patches_ex(self._ensure_engine(), _lib.ptr(a), dt, N, H, W, Cc, C.byref(cw),
+                                                    C.byref(cn), int(cols), out_channel, _lib.ptr(prob),
+                                                    _lib.ptr(mask)))
         return prob, mask
 
 

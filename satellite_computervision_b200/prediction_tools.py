@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from .model_tools import UNetModel
-from .processing import NormalizedTensor, NormSpec
+from .processing import TILE_STAT_MODES, NormalizedTensor, NormSpec
 
 
 def generate_chip_indices(arr, buff=128, kernel=256):
@@ -66,6 +66,13 @@ def predict_chips(arr, chip_indices, template, m, kernel=256, buff=128, norm=Non
         return template
     y_buff = x_buff = buff // 2
     if chip_indices == generate_chip_indices(raw, buff, kernel):
+        direct = (isinstance(template, np.ndarray) and template.shape == raw.shape[:2] and template.flags.c_contiguous
+                  and template.flags.writeable and template.dtype in (np.float32, np.float64))
+        if direct:
+            # the stitch kernel does `template[core] += p` itself, in the template's own dtype (float64 as at :769)
+            m.predict_mosaic(raw, buff=buff, kernel=kernel, norm=norm, out_channel=channel, want_mask=False,
+                             out_prob=template, accumulate=True)
+            return template
         prob, _ = m.predict_mosaic(raw, buff=buff, kernel=kernel, norm=norm, out_channel=channel, want_mask=False)
         ys = sorted({y for y, _ in chip_indices})
         xs = sorted({x for _, x in chip_indices})
@@ -177,7 +184,10 @@ def geotiff_predictions(imageDataset, model, jsonFile, kernel_buffer=[128, 128],
     ppr, tp = mixer['patchesPerRow'], mixer['totalPatches']
     kernel_shape = mixer['patchDimensions']
     x, n = _collect(imageDataset, tp)
-    prob, _ = model.predict_patches(x, ppr, kernel_shape, kernel_buffer, norm=norm or n, out_channel=0)
+    # this stitcher has its own window (:503-506, :520): rows [kb[1]/2, kb[1]/2 + ks[0]), cols [kb[0]/2, kb[0]/2 + ks[1])
+    x_buffer, y_buffer = int(kernel_buffer[0] / 2), int(kernel_buffer[1] / 2)
+    crop = (y_buffer, y_buffer + kernel_shape[0], x_buffer, x_buffer + kernel_shape[1])
+    prob, _ = model.predict_patches(x, ppr, kernel_shape, kernel_buffer, norm=norm or n, out_channel=0, crop=crop)
     proj = mixer.get('projection', {})
     return prob[..., None], proj.get('affine', {}).get('doubleMatrix'), proj.get('crs')
 
@@ -255,8 +265,16 @@ def predict_overlap_chunks(chw, m, chunk=256, depth=64, norm=None):
     ``map_overlap(depth=(0,64,64), boundary=0)``) + ``predict_chunk`` (``utils/model_tools.py:1295-1300``):
     every ``chunk``^2 block of the (C,H,W) raster is predicted with a ``depth`` halo of neighbour data,
     zeros beyond the raster edge, and the halo is trimmed.  H and W must be multiples of ``chunk``
-    (``trim_dataArray``, ``utils/pc_tools.py:109-129``).  Returns (H, W) of probability channel 0."""
+    (``trim_dataArray``, ``utils/pc_tools.py:109-129``).  Returns (H, W) of probability channel 0.
+
+    The reference normalises the raster first (``normalize_dataArray``, ``:757-758`` / ``:809``) and dask then pads
+    the NORMALISED data with exact zeros, so with ``norm=`` (or a NormalizedTensor) the halo beyond the raster
+    edge is zero AFTER normalisation: the gather kernel gets the valid window and emits zeros outside it.
+    Per-tile statistics would see the padding and are rejected."""
     m = _model(m)
+    chw, norm = UNetModel._split_norm(chw, norm)
+    if norm is not None and norm.mode in TILE_STAT_MODES:
+        raise ValueError('per-tile statistics cannot be combined with zero-padded overlap chunks')
     chw = np.asarray(chw)
     Cc, H, W = chw.shape
     if H % chunk or W % chunk:
@@ -264,22 +282,30 @@ def predict_overlap_chunks(chw, m, chunk=256, depth=64, norm=None):
     hwc = np.zeros((H + 2 * depth + chunk, W + 2 * depth + chunk, Cc), dtype=chw.dtype)
     hwc[depth:depth + H, depth:depth + W] = np.moveaxis(chw, 0, -1)
     # a zero-padded mosaic whose chip grid (buff = 2*depth, kernel = chunk) covers exactly [0,H)x[0,W)
-    prob, _ = m.predict_mosaic(hwc, buff=2 * depth, kernel=chunk, norm=norm, want_mask=False)
-    return prob[depth:depth + H, depth:depth + W]
+    prob, _ = m.predict_mosaic(hwc, buff=2 * depth, kernel=chunk, norm=norm, want_mask=False,
+                               valid=(depth, depth + H, depth, depth + W))
+    return np.array(prob[depth:depth + H, depth:depth + W])
 
 
 def _extract_debug(hwc, norm, device=0):
-    """K1 alone on one (H,W,C) image treated as a single chip (test / NormalizedTensor.numpy)."""
+    """K1 alone on one (H,W,C) image (tests / NormalizedTensor materialisation): the bf16-rounded network
+    input, widened to float32.  A square image is one chip; other shapes are cut into gcd(H, W) squares, which
+    is exact for every normaliser except the per-tile statistics (those need the whole image as one tile)."""
     lib = _lib.load_library()
     a, dt = _lib.as_input(hwc)
     H, W, Cc = a.shape
-    if H != W:
-        raise ValueError('square images only')
-    t = _lib.Tiling(H, 0)
+    side = H if H == W else int(np.gcd(H, W))
+    if side != H and norm is not None and norm.mode in TILE_STAT_MODES:
+        raise ValueError('per-tile statistics can only be materialised for square images')
+    t = _lib.Tiling(side, 0)
     cn = (norm or NormSpec()).to_c(Cc)
-    idx = np.array([[0, 0]], dtype=np.int32)
+    idx = np.array([[y, x] for y in range(0, H, side) for x in range(0, W, side)], dtype=np.int32)
     cpad = C.c_int()
-    out = np.empty((1, H, W, _lib.SCV_MAX_BANDS), dtype=np.float32)
-    _lib.check(lib.scv_debug_extract(device, _lib.ptr(a), dt, H, W, Cc, C.byref(t), C.byref(cn), _lib.ptr(idx), 1,
+    out = np.empty((len(idx), side, side, _lib.SCV_MAX_BANDS), dtype=np.float32)
+    _lib.check(lib.scv_debug_extract(device, _lib.ptr(a), dt, H, W, Cc, C.byref(t), C.byref(cn), _lib.ptr(idx), len(idx),
                                      _lib.ptr(out), C.byref(cpad)))
-    return out.reshape(-1)[:H * W * cpad.value].reshape(H, W, cpad.value)[..., :Cc].copy()
+    tiles = out.reshape(-1)[:len(idx) * side * side * cpad.value].reshape(len(idx), side, side, cpad.value)[..., :Cc]
+    res = np.empty((H, W, Cc), dtype=np.float32)
+    for (y, x), tl in zip(idx, tiles):
+        res[y:y + side, x:x + side] = tl
+    return res

@@ -11,6 +11,9 @@ from collections import namedtuple
 
 Band = namedtuple('Band', 'rank world tile_row_begin tile_row_end n_tile_cols src_row0 src_row1 dst_row0 dst_row1 '
                           'dst_col0 dst_col1 n_chips')
+# tile-balanced shard: chips [tile_begin, tile_end) of the row-major chip list; the tile rows it touches may be partial
+Shard = namedtuple('Shard', 'rank world tile_begin tile_end n_tile_cols tile_row_begin tile_row_end src_row0 src_row1 '
+                            'dst_row0 dst_row1 n_chips kernel')
 
 
 def chip_grid(H, W, kernel=256, buff=128):
@@ -42,6 +45,74 @@ def rank_band(H, W, kernel, buff, rank, world):
     else:
         src0 = src1 = dst0 = dst1 = c0 = c1 = 0
     return Band(rank, world, r0, r1, len(xs), src0, src1, dst0, dst1, c0, c1, (r1 - r0) * len(xs))
+
+
+def rank_shard(H, W, kernel, buff, rank, world):
+    """Tile-balanced sharding (hard part 7): rank r takes chips [r*n/world, (r+1)*n/world) of the
+    row-major chip list, so every rank gets n/world chips +-1 (1764 chips over 8 ranks: 220 / 221) instead of
+    whole tile rows (6,6,5,5,5,5,5,5 rows = 252 vs 210 chips).  src / dst rows are the mosaic rows read and the
+    output rows written by the tile rows the range touches (the first and last may be shared with a neighbour,
+    each rank writing only its own cores)."""
+    ys, xs = chip_grid(H, W, kernel, buff)
+    n, ncols = len(ys) * len(xs), len(xs)
+    t0, t1 = (n * rank) // world, (n * (rank + 1)) // world
+    half, side = buff // 2, kernel + buff
+    if t1 > t0:
+        r0, r1 = t0 // ncols, (t1 - 1) // ncols + 1
+        src0, src1 = ys[r0] - half, ys[r1 - 1] - half + side
+        dst0, dst1 = ys[r0], ys[r1 - 1] + kernel
+    else:
+        r0 = r1 = src0 = src1 = dst0 = dst1 = 0
+    return Shard(rank, world, t0, t1, ncols, r0, r1, src0, src1, dst0, dst1, t1 - t0, kernel)
+
+
+def shard_rects(shard, H, W, buff):
+    """Output rectangles (y0, y1, x0, x1) a shard writes: one per tile row it touches (cores only)."""
+    ys, xs = chip_grid(H, W, shard.kernel, buff)
+    out = []
+    for r in range(shard.tile_row_begin, shard.tile_row_end):
+        c0 = shard.tile_begin - r * shard.n_tile_cols if r == shard.tile_row_begin else 0
+        c1 = shard.tile_end - r * shard.n_tile_cols if r == shard.tile_row_end - 1 else shard.n_tile_cols
+        c0, c1 = max(c0, 0), min(c1, shard.n_tile_cols)
+        if c1 > c0:
+            out.append((ys[r], ys[r] + shard.kernel, xs[c0], xs[c1 - 1] + shard.kernel))
+    return out
+
+
+def gather_shards(rows, shard, H, W, buff, dst=0, group=None):
+    """Optional final collective for tile-balanced shards: every rank's output rows [dst_row0, dst_row1) (a
+    (rows, W) tensor holding its cores) are gathered on rank `dst` and its rectangles pasted into the (H, W)
+    raster.  All transfers are posted as ONE batch of point-to-point operations (`batch_isend_irecv` =
+    ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd on NCCL; NVSwitch gives every peer full bandwidth, so a
+    flat gather is optimal -- SURVEY 8(e))."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if rank != dst:
+        if shard.n_chips > 0:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, rows.contiguous(), dst, group)]):
+                w.wait()
+        return None
+    full = torch.zeros((H, W), dtype=rows.dtype, device=rows.device)
+    bufs, ops = {}, []
+    for r in range(world):
+        sh = rank_shard(H, W, shard.kernel, buff, r, world)
+        if sh.n_chips == 0:
+            continue
+        if r == dst:
+            bufs[r] = (sh, rows)
+            continue
+        buf = torch.empty((sh.dst_row1 - sh.dst_row0, W), dtype=rows.dtype, device=rows.device)
+        bufs[r] = (sh, buf)
+        ops.append(dist.P2POp(dist.irecv, buf, r, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for r, (sh, buf) in bufs.items():
+        for y0, y1, x0, x1 in shard_rects(sh, H, W, buff):
+            full[y0:y1, x0:x1] = buf[y0 - sh.dst_row0:y1 - sh.dst_row0, x0:x1]
+    return full
 
 
 def gather_mosaic(band_rows, band, H, W, dst=0, group=None):

@@ -22,7 +22,7 @@ def lib():
 def test_exports_every_declared_symbol(lib):
     header = open(os.path.join(ROOT, 'include', 'scv.h')).read()
     declared = re.findall(r'SCV_API\s+[\w\s\*]+?\b(scv_\w+)\s*\(', header)
-    assert len(declared) >= 19
+    assert len(declared) >= 25
     assert sorted(declared) == sorted(_lib.PROTOTYPES)
     for name in declared:
         assert hasattr(lib, name), name
@@ -32,8 +32,10 @@ def test_exports_every_declared_symbol(lib):
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Config) == 4 * (5 + 8 + 3)
     assert C.sizeof(_lib.Tensor) == 8 + 8 + 32
-    assert C.sizeof(_lib.Norm) == 8 + 2 * 16 * 4
+    assert C.sizeof(_lib.Norm) == 8 + 2 * 16 * 4 + 4 + 16 * 4
     assert C.sizeof(_lib.Tiling) == 8
+    assert C.sizeof(_lib.MosaicOpts) == 4 * 9
+    assert C.sizeof(_lib.Crop) == 16
     assert C.sizeof(_lib.Times) == 4 * 4 + 4 * 4 + 64 * 4 + 64 * 8
 
 

@@ -1,0 +1,133 @@
+"""GPU parity ON THE BASELINE CONFIGURATIONS, through the public API / C-ABI and the same host path
+bench.py times (mosaic call, max_batch = 126, three-stream H2D / compute / D2H pipeline):
+
+* BASELINE configs[0]: 2048 x 2048 x 6 uint16 raster, variant-A network at full size, all 49 chips against the
+  oracle's reference loop (generate_chip_indices + batch-1 predict + crop + `+=`);
+* variant B (get_unet_model as written) at full size; the NAIP substitute of configs[3]
+  (768 x 768 x 3 uint8 tiles, 512 kernel + 256 buffer, /255);
+* a slice of the 10980-wide bench scene with the bench's own weights.
+
+Bars (north_star): placement / zeros bit-exact, max |dp| <= 1e-2, mask agreement >= 99.9 %.
+"""
+import numpy as np
+import pytest
+
+from oracle import normalize as onorm
+from oracle import tiling as otile
+from oracle import unet as ounet
+from satellite_computervision_b200 import model_tools, prediction_tools as pt, processing
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-2
+MASK_AGREE = 0.999
+
+
+def _report(tag, got, ref, thr=0.5):
+    d = np.abs(got - ref)
+    core = ref != 0
+    margin = np.abs(ref[core] - thr)
+    hist = np.histogram(margin, bins=[0, 1e-4, 1e-3, 2.5e-3, 1e-2, 5e-2, 1.0])[0] / max(1, margin.size)
+    agree = ((got > thr) == (ref > thr))[core].mean()
+    print(f'{tag}: max|dp| {d.max():.3e}  mean|dp| {d[core].mean():.3e}  mask agreement {agree:.5f}  '
+          f'|p-thr| histogram [<1e-4,<1e-3,<2.5e-3,<1e-2,<5e-2,rest] = {np.round(hist, 4).tolist()}')
+    return d.max(), agree
+
+
+def test_config1_2048_raster_all_chips_match_reference_loop():
+    """BASELINE configs[0] exactly as SURVEY 8(d) pins it: rng(0) uint16 DN in [0, 10000), model input
+    rescale_tensor(moments=[(0,10000)]*6), 7x7 = 49 chips of 384^2, float64 template, predict_chips."""
+    specs = ounet.weight_specs('A', 6, 1)
+    w = ounet.init_weights(specs, seed=0, randomize_bn=True, head_bias=0.0)
+    m = model_tools.binary_unet(nchannels=6, max_batch=126, outputs='probs')
+    m.set_weights(w)
+    rng = np.random.default_rng(0)
+    dn = rng.integers(0, 10000, (2048, 2048, 6), dtype=np.uint16)
+    mm = [(0, 10000)] * 6
+    idx = pt.generate_chip_indices(dn, 128, 256)
+    assert idx == otile.generate_chip_indices(dn.shape, 128, 256) and len(idx) == 49
+    template = np.zeros((2048, 2048))                                  # float64 like :769
+    got = pt.predict_chips(processing.rescale_tensor(dn, moments=mm), idx, template, m, 256, 128)
+    assert got is template and got.dtype == np.float64
+    x = onorm.rescale_tensor(dn.astype(np.float32), moments=mm)
+    ref = otile.predict_chips(x, idx, np.zeros((2048, 2048)), ounet.make_predict_fn(w, variant='A'), 256, 128)
+    assert np.array_equal(got == 0, ref == 0)                           # footprint: cores written, margins untouched
+    assert np.all(got[:64] == 0) and np.all(got[:, :64] == 0) and np.all(got[1856:] == 0) and np.all(got[:, 1856:] == 0)
+    err, agree = _report('config 1 (2048^2, 49 chips, variant A)', got, ref)
+    assert err <= PROB_TOL and agree >= MASK_AGREE
+    # the mask raster of the same call is the strict threshold of the stitched probabilities
+    prob, mask = m.predict_mosaic(dn, 128, 256, norm=processing.rescale_spec(6, moments=mm))
+    assert np.array_equal(prob.astype(np.float64), got) and np.array_equal(mask, (prob > 0.5).astype(np.uint8))
+    assert m.times()['n_tiles'] == 49
+
+
+def test_variant_b_full_size_matches_oracle():
+    """get_unet_model as written (one conv per encoder block, softmax head + argmax) at full filter widths."""
+    specs = ounet.weight_specs('B', 6, 2)
+    w = ounet.init_weights(specs, seed=2, randomize_bn=True)
+    m = model_tools.get_unet_model(2, 6)
+    m.set_weights(w)
+    rng = np.random.default_rng(3)
+    dn = rng.integers(0, 10000, (2, 384, 384, 6), dtype=np.uint16)
+    x = dn.astype(np.float32) / np.float32(10000.0)
+    ref_p, ref_c = ounet.forward(x, w, 'B', head='softmax')
+    probs, classes = m.predict(dn, norm=processing.scalar_spec(6, 10000.0))
+    assert classes.dtype == np.int32 and classes.shape == ref_c.shape
+    err = np.abs(probs - ref_p).max()
+    agree = (classes == ref_c).mean()
+    margin = np.abs(ref_p[..., 0] - ref_p[..., 1])
+    print('variant B full size: max|dp|', err, 'class agreement', agree, 'frac with margin < 1e-2', (margin < 1e-2).mean())
+    assert err <= PROB_TOL and agree >= MASK_AGREE
+
+
+def test_naip_768_uint8_variant_a_matches_reference_loop():
+    """Substitute for BASELINE configs[3]: 3-band NAIP-like uint8 raster, /255,
+    512 px kernel + 256 px buffer -> 768^2 chips (parking notebook cells 16, 40, 58)."""
+    specs = ounet.weight_specs('A', 3, 1)
+    w = ounet.init_weights(specs, seed=4, randomize_bn=True, head_bias=0.0)
+    m = model_tools.binary_unet(nchannels=3, max_batch=8, outputs='probs')
+    m.set_weights(w)
+    rng = np.random.default_rng(5)
+    H = W = 128 + 2 * 512 + 700
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    idx = pt.generate_chip_indices(img, 256, 512)
+    assert len(idx) == 4
+    got = pt.predict_chips(img, idx, np.zeros((H, W)), m, 512, 256, norm=processing.scalar_spec(3, 255.0))
+    ref = otile.predict_chips(onorm.scalar_rescale(img.astype(np.float32), np.float32(255.0)), idx, np.zeros((H, W)),
+                              ounet.make_predict_fn(w, variant='A'), 512, 256)
+    assert np.array_equal(got == 0, ref == 0)
+    err, agree = _report('NAIP 768^2 x3 uint8 (variant A)', got, ref)
+    assert err <= PROB_TOL and agree >= MASK_AGREE
+
+
+def test_bench_scene_slice_matches_oracle():
+    """One tile row of the 10980-wide bench scene (bench.make_scene / bench.random_weights, the exact inputs
+    bench.py times) through the host-buffer mosaic path with the bench's batch size, 8 chips checked."""
+    import bench
+    H, W = 64 + 256 + 192 + 1, bench.SCENE
+    scene = bench.make_scene(H, W, seed=1)
+    m = model_tools.binary_unet(nchannels=6, max_batch=126, outputs='probs')
+    w = bench.random_weights(m, seed=0)
+    m.set_weights(w)
+    spec = processing.rescale_spec(6, moments=[(0, 10000)] * 6)
+    prob, mask = m.predict_mosaic(scene, 128, 256, norm=spec)
+    idx = pt.generate_chip_indices(scene, 128, 256)
+    assert len(idx) == 42
+    pick = [idx[i] for i in (0, 1, 7, 13, 20, 29, 40, 41)]
+    x = onorm.rescale_tensor(scene.astype(np.float32), moments=[(0, 10000)] * 6)
+    ref = otile.predict_chips(x, pick, np.zeros((H, W)), ounet.make_predict_fn(w, variant='A'), 256, 128)
+    sel = ref != 0
+    got = np.where(sel, prob, 0)
+    err, agree = _report('bench scene slice (8 of 42 chips)', got, ref)
+    assert err <= PROB_TOL and agree >= MASK_AGREE
+    assert np.array_equal(mask[sel], (prob[sel] > 0.5).astype(np.uint8))
+
+
+def test_real_keras_model_matches_oracle_when_tensorflow_is_present():
+    """the float arithmetic of the oracle is a restatement of Keras.  When TensorFlow imports on the
+    box, pin it: build the reference's own layer stack with tf.keras and compare one forward pass."""
+    tf = pytest.importorskip('tensorflow')
+    from oracle import keras_probe
+    err = keras_probe.compare(tf)
+    print('oracle vs tf.keras: max|dp|', err)
+    assert err <= 1e-4

@@ -53,8 +53,22 @@ def test_normaliser_constants_reproduce_reference_bits(golden_dir):
     assert isinstance(lazy, processing.NormalizedTensor) and lazy.raw is not None
     assert processing.rescale_spec(6).mode == _lib.SCV_NORM_PIXEL_MINMAX          # reference default axes=[2]
     assert processing.normalize_spec(6, axes=[0, 1]).mode == _lib.SCV_NORM_TILE_ZSCORE
+    assert processing.rescale_spec(6, axes=[0, 1, 2]).mode == _lib.SCV_NORM_TILE_GLOBAL_MINMAX
+    assert processing.normalize_spec(6, axes=[0, 1, 2]).mode == _lib.SCV_NORM_TILE_GLOBAL_ZSCORE
+    sp = processing.normalize_spec(6, splits=[2, 3])                              # data-derived, channel 5 passes through
+    c = sp.to_c(6)
+    assert (c.ngroups, c.group_size[0], c.group_size[1]) == (2, 2, 3)
+    assert processing.band_zscore_spec().mode == _lib.SCV_NORM_PIXEL_ZSCORE_SD
+    # a length-1 moments list broadcasts over the channels like the reference's numpy arrays do (:304-311)
+    one = processing.rescale_spec(6, moments=[(0, 10000)])
+    assert np.array_equal(one.sub, np.zeros(6, np.float32)) and one.div.shape == (6,)
+    # derived / one-hot planes appended after the rescaled bands pass through, whatever the rescale mode
+    wide = processing.rescale_spec(4).with_passthrough(4, 6)
+    assert wide.groups == [4] and wide.mode == _lib.SCV_NORM_PIXEL_MINMAX
+    widem = processing.rescale_spec(4, moments=[(0, 2)] * 4).with_passthrough(4, 6)
+    assert np.array_equal(widem.sub[4:], [0, 0]) and np.array_equal(widem.div[4:], [1, 1])
     with pytest.raises(NotImplementedError):
-        processing.rescale_spec(6, axes=[0, 1, 2])
+        processing.rescale_spec(6, axes=[0])
     with pytest.raises(ValueError):
         processing.rescale_spec(6, moments=[(0, 1)] * 5)
 

@@ -81,3 +81,57 @@ def test_gloo_row_band_sharding_and_gather(tmp_path, world):
     idx = otile.generate_chip_indices((H, W, 3), buff, kernel)
     want = otile.predict_chips(scene, idx, np.zeros((H, W)), lambda b: b.mean(-1, keepdims=True), kernel, buff)
     assert np.array_equal(full, want.astype(np.float32))
+
+
+def test_tile_balanced_shards_partition_the_chip_list():
+    """SURVEY 7 hard part 7: 1764 chips over 8 ranks = 220 / 221 each (whole tile rows would give 252 / 210)."""
+    H = W = 10980
+    idx = otile.generate_chip_indices((H, W, 6), 128, 256)
+    shards = [sharding.rank_shard(H, W, 256, 128, r, 8) for r in range(8)]
+    assert [s.n_chips for s in shards] == [220, 221, 220, 221, 220, 221, 220, 221]
+    assert shards[0].tile_begin == 0 and shards[-1].tile_end == len(idx)
+    assert all(a.tile_end == b.tile_begin for a, b in zip(shards, shards[1:]))
+    cover = np.zeros((H // 4, W // 4), np.int8)  # rectangles are multiples of 64: check on a 4x coarser grid
+    for s in shards:
+        chips = idx[s.tile_begin:s.tile_end]
+        assert s.src_row0 == chips[0][0] - 64 and s.src_row1 == chips[-1][0] + 320
+        assert s.dst_row0 == chips[0][0] and s.dst_row1 == chips[-1][0] + 256
+        rects = sharding.shard_rects(s, H, W, 128)
+        assert sum((y1 - y0) * (x1 - x0) for y0, y1, x0, x1 in rects) == s.n_chips * 256 * 256
+        for y0, y1, x0, x1 in rects:
+            cover[y0 // 4:y1 // 4, x0 // 4:x1 // 4] += 1
+    assert cover.max() == 1 and cover[16:16 + 42 * 64, 16:16 + 42 * 64].min() == 1 and cover.sum() == (42 * 64) ** 2
+    one = sharding.rank_shard(500, 500, 256, 128, 1, 2)  # a single chip: rank 1 has nothing
+    assert one.n_chips + sharding.rank_shard(500, 500, 256, 128, 0, 2).n_chips == 1
+
+
+def _shard_worker(rank, world, port, H, W, kernel, buff, out_path):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        scene = np.random.default_rng(0).random((H, W, 3)).astype(np.float32)
+        sh = sharding.rank_shard(H, W, kernel, buff, rank, world)
+        rows = np.zeros((sh.dst_row1 - sh.dst_row0, W), np.float32)
+        # stand-in for the device call (NOT a product path): per-pixel band mean written to this shard's cores only
+        for y0, y1, x0, x1 in sharding.shard_rects(sh, H, W, buff):
+            rows[y0 - sh.dst_row0:y1 - sh.dst_row0, x0:x1] = scene[y0:y1, x0:x1].mean(-1)
+        full = sharding.gather_shards(torch.from_numpy(rows), sh, H, W, buff, dst=0)
+        if rank == 0:
+            np.save(out_path, full.numpy())
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_gloo_tile_balanced_sharding_and_batched_gather(tmp_path, world):
+    H, W, kernel, buff = 420, 300, 32, 16
+    out = str(tmp_path / 'full.npy')
+    mp.spawn(_shard_worker, args=(world, _free_port(), H, W, kernel, buff, out), nprocs=world, join=True)
+    full = np.load(out)
+    scene = np.random.default_rng(0).random((H, W, 3)).astype(np.float32)
+    idx = otile.generate_chip_indices((H, W, 3), buff, kernel)
+    want = otile.predict_chips(scene, idx, np.zeros((H, W)), lambda b: b.mean(-1, keepdims=True), kernel, buff)
+    assert np.array_equal(full, want.astype(np.float32))
