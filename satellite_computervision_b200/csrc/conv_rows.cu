@@ -30,6 +30,8 @@ cudaError_t rows_attr() {
 
 cudaError_t conv_rows_launch(const ConvLaunch& L, cudaStream_t s) {
   if (L.p.ntaps != 9 || L.p.W % kRowsPx || (L.p.H & 1)) return cudaErrorInvalidValue;
+  if (L.KC == 16 && L.BN == 32) return rows_epi<16, 32>(L, s);  // first layer: 8 stored channels, zero-filled to 16 by TMA
+  if (L.KC == 16 && L.BN == 64) return rows_epi<16, 64>(L, s);
   if (L.KC == 32 && L.BN == 32) return rows_epi<32, 32>(L, s);
   if (L.KC == 32 && L.BN == 64) return rows_epi<32, 64>(L, s);
   if (L.KC == 64 && L.BN == 32) return rows_epi<64, 32>(L, s);
@@ -39,6 +41,8 @@ cudaError_t conv_rows_launch(const ConvLaunch& L, cudaStream_t s) {
 
 cudaError_t conv_rows_init_attributes() {
   cudaError_t e;
+  if ((e = rows_attr<16, 32>()) != cudaSuccess) return e;
+  if ((e = rows_attr<16, 64>()) != cudaSuccess) return e;
   if ((e = rows_attr<32, 32>()) != cudaSuccess) return e;
   if ((e = rows_attr<32, 64>()) != cudaSuccess) return e;
   if ((e = rows_attr<64, 32>()) != cudaSuccess) return e;

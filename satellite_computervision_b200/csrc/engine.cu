@@ -262,6 +262,9 @@ struct LayerDef {
   float* d_skip_s = nullptr;
   float* d_skip_t = nullptr;
   CUtensorMap tmB;
+  // 8-channel first layer, row-kernel form: the same weights as [Cout][tap * 16 + c] (channels 8..15 zero); the
+  // activation keeps its 8-channel pitch and TMA zero-fills the upper half of every 16-channel box
+  __nv_bfloat16* d_w16 = nullptr;
 };
 
 struct Arch {
@@ -540,6 +543,16 @@ static int upload_layer(LayerDef& l, const std::vector<float>& w /*[ntotal][ktot
     CUDA_TRY(cudaMemcpy(l.d_skip_s, skip_s->data(), skip_s->size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(l.d_skip_t, skip_t->data(), skip_t->size() * 4, cudaMemcpyHostToDevice));
   }
+  if (l.KC == 8 && l.kind == L_CONV3) {
+    std::vector<__nv_bfloat16> w16((size_t)l.ntotal * 144, __float2bfloat16_rn(0.f));
+    for (int o = 0; o < l.ntotal; ++o)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int c = 0; c < 8; ++c) w16[(size_t)o * 144 + tap * 16 + c] = wb[(size_t)o * ktotal + tap * 8 + c];
+    if (l.d_w16) cudaFree(l.d_w16);
+    l.d_w16 = nullptr;
+    CUDA_TRY(cudaMalloc(&l.d_w16, w16.size() * 2));
+    CUDA_TRY(cudaMemcpy(l.d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+  }
   return make_w_tmap(&l.tmB, l.d_w, (int)ktotal, l.ntotal, l.KC, l.BN);
 }
 
@@ -686,12 +699,14 @@ static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* 
 static bool plan_rows(const LayerDef& l, int h, int w, int ncls, int* nslab) {
   if (!env_int("SCV_ROWS", 1)) return false;
   if (l.kind != L_CONV3 || w % kRowsPx || (h & 1)) return false;
-  if (l.KC != 32 && l.KC != 64) return false;
+  const bool first = l.KC == 8 && l.d_w16 != nullptr && env_int("SCV_ROWS_FIRST", 1);  // 8 stored channels read as 16
+  if (l.KC != 32 && l.KC != 64 && !first) return false;
   if (l.ntotal != l.cout || (l.cout != 32 && l.cout != 64)) return false;
   if (l.epi != EPI_STORE && l.epi != EPI_POOL_SKIP && l.epi != EPI_HEAD) return false;
-  const int chunks = l.cin_pad / l.KC;
+  const int kc = first ? 16 : l.KC, cin = first ? 16 : l.cin_pad;
+  const int chunks = cin / kc;
   for (int ns = std::max(6, 4 * chunks); ns >= 2 * chunks && ns >= 3; --ns)  // slabs of two input rows each
-    if (rows_smem_bytes(l.KC, l.cout, l.cin_pad, ns, l.epi, ncls) <= kSlabSmemBudget) {
+    if (rows_smem_bytes(kc, l.cout, cin, ns, l.epi, ncls) <= kSlabSmemBudget) {
       *nslab = ns;
       return true;
     }
@@ -719,7 +734,11 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   L->EPI = l.epi;
   int bn = 0, ns = 0, nacc = 2;
   if (plan_rows(l, h, w, e ? e->arch.cfg.nclasses : 1, &ns)) {
+    const bool first = l.KC == 8;  // 8-channel input: boxes of 16 channels, the upper 8 zero-filled by TMA (out of bounds)
+    const int kc = first ? 16 : l.KC, cin = first ? 16 : l.cin_pad;
     L->slab = 2;
+    L->KC = kc;
+    p.Cin = cin;
     p.dbg = env_int("SCV_ROWS_DBG", 0);
     L->BN = l.cout;
     L->nacc = kRowsEpiGroups;
@@ -730,14 +749,15 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     p.n_tiles_n = 1;
     p.nslab = ns;
     // issuers in flight must not exceed the reuse distance (in row pairs) of a slab slot or an accumulator pair
-    p.n_issuers = std::max(1, std::min({kRowsIssuers, ns / (l.cin_pad / l.KC), 256 / l.cout,
+    p.n_issuers = std::max(1, std::min({kRowsIssuers, ns / (cin / kc), 256 / l.cout,
                                         env_int("SCV_ROWS_ISSUERS", kRowsIssuers)}));
     const long long pairs = (long long)B * p.tiles_x * (h / 2);
     L->grid = (int)std::min<long long>(sm_count(), pairs);
-    L->smem = rows_smem_bytes(l.KC, l.cout, l.cin_pad, ns, l.epi, e ? e->arch.cfg.nclasses : 1);
-    if (l.BN != l.cout) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, l.cout));
+    L->smem = rows_smem_bytes(kc, l.cout, cin, ns, l.epi, e ? e->arch.cfg.nclasses : 1);
+    if (first) SCV_TRY(make_w_tmap(&L->tmB, l.d_w16, 144, l.ntotal, 16, l.cout));
+    else if (l.BN != l.cout) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, l.cout));
     else L->tmB = l.tmB;
-    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, kRowsSlabPx, 2, 1));
+    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, kc, kRowsSlabPx, 2, 1));
     return SCV_OK;
   }
   // weight-streaming halo-slab kernel: Cout = 128 layers whose 3x3 weights exceed shared memory (conv_slabw.cuh);
@@ -1388,6 +1408,7 @@ void scv_engine_destroy(scv_engine* e) {
   for (auto& pl : e->plans) cudaFree(pl->arena);
   for (auto& l : e->arch.layers) {
     cudaFree(l.d_w);
+    cudaFree(l.d_w16);
     cudaFree(l.d_bias);
     cudaFree(l.d_skip_s);
     cudaFree(l.d_skip_t);
@@ -1988,6 +2009,7 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
     cudaFree(d_f);
     cudaFree(d_err);
     cudaFree(l.d_w);
+    cudaFree(l.d_w16);
     cudaFree(l.d_bias);
     cudaFree(l.d_skip_s);
     cudaFree(l.d_skip_t);
@@ -2125,7 +2147,7 @@ int scv_debug_extract(int device, const void* hwc, int dtype, int H, int W, int 
   const int row_bytes = side * C * dtype_bytes(dtype);
   ep.rows_per_block = std::max(1, std::min(8, (44 * 1024) / (row_bytes + 32)));
   ep.out = d_out;
-  if (ep.norm_mode == SCV_NORM_TILE_ZSCORE || ep.norm_mode == SCV_NORM_TILE_MINMAX) {
+  if (tile_stats_mode(ep.norm_mode)) {
     DBG_TRY(cudaMalloc(&d_stats, (size_t)n_tiles * C * 2 * sizeof(float)));
     TileStatsParams sp{};
     sp.src = ep.src;
@@ -2138,6 +2160,8 @@ int scv_debug_extract(int device, const void* hwc, int dtype, int H, int W, int 
     sp.mode = ep.norm_mode;
     sp.eps = ep.div[0];
     sp.stats = d_stats;
+    sp.ngroups = ep.ngroups;
+    for (int c = 0; c < SCV_MAX_BANDS; ++c) sp.group_end[c] = ep.group_end[c];
     DBG_TRY(launch_tile_stats(sp, n_tiles, 0));
     ep.tile_stats = d_stats;
   }

@@ -130,9 +130,7 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
 
   const int nchunk = p.cpad >> 3;
   const int mode = p.norm_mode;
-  const float* st = (mode == SCV_NORM_TILE_ZSCORE || mode == SCV_NORM_TILE_MINMAX)
-                        ? p.tile_stats + static_cast<size_t>(tile) * C * 2
-                        : nullptr;
+  const float* st = p.tile_stats != nullptr ? p.tile_stats + static_cast<size_t>(tile) * C * 2 : nullptr;  // SCV_NORM_TILE_*
   for (int rr = 0; rr < nrows; ++rr) {
     const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(g_first + rr * pitch) & 15);
     const uint8_t* srow = sm + rr * sstride + mis;
@@ -678,6 +676,8 @@ cudaError_t launch_stitch(const StitchParams& p, int n_tiles, cudaStream_t s) {
   int px = 1;
   if (!(p.force_scalar & 1) && aligned(4)) px = 4;
   if (px == 4 && !(p.force_scalar & 2) && aligned(8)) px = 8;
+  if (const char* o = getenv("SCV_K4_PX"))  // experiments: cap the pixels per thread
+    if (atoi(o) > 0 && atoi(o) < px) px = atoi(o) >= 4 ? 4 : 1;
   if (p.prob_f64) return p.accumulate ? launch_stitch_t<double, true>(p, n_tiles, px, s) : launch_stitch_t<double, false>(p, n_tiles, px, s);
   return p.accumulate ? launch_stitch_t<float, true>(p, n_tiles, px, s) : launch_stitch_t<float, false>(p, n_tiles, px, s);
 }
