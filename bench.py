@@ -296,7 +296,7 @@ def main():
         return float(t.item())
 
     H = W = args.scene
-    model = model_tools.binary_unet(nchannels=BANDS, device=local_rank, max_batch=args.max_batch, outputs='probs')
+    model = model_tools.binary_unet(nchannels=BANDS, device=local_rank, max_batch=args.max_batch, outputs='probs', seed=0)
     model.set_weights(random_weights(model, seed=0))
     spec = processing.rescale_spec(BANDS, moments=[(0, 10000)] * BANDS)
     lib = model._lib

@@ -210,8 +210,9 @@ SCV_API int scv_predict_patches(scv_engine* e, const void* nhwc, int dtype, int 
                         float* out_prob, uint8_t* out_mask);
 
 /* scv_predict_mosaic with chip-range sharding, float64 / accumulating output and a valid window (see
- * scv_mosaic_opts).  out_prob is H*W elements of opts->out_dtype.  Host buffers that are not page-locked are
- * registered for the duration of the call (cudaHostRegister) so the copies overlap the compute. */
+ * scv_mosaic_opts).  out_prob is H*W elements of opts->out_dtype.  Page-locked host buffers
+ * (scv_host_alloc) give full H2D / compute / D2H overlap; pageable ones work through staged copies that are
+ * interleaved with the kernel launches (scv_set_option "host_register" = 1 page-locks them for the call instead). */
 SCV_API int scv_predict_mosaic_ex(scv_engine* e, const void* hwc, int dtype, int H, int W, int C,
                           const scv_tiling* tiling, const scv_norm* norm, const scv_mosaic_opts* opts,
                           void* out_prob, uint8_t* out_mask);

@@ -475,6 +475,37 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             const uint32_t row0 = smem_u32(stage) + lane * 64;
             float v[32];
             uint32_t pk[16], w0[16];
+            if constexpr (EPI == EPI_STORE && COUT == 32) {
+              if (p.linear_out) {
+                // dense output: LINEAR staging (pixel-major, 64 B per pixel) and one plain 2 KB bulk store per
+                // row; bank conflicts are avoided by rotating which 16-byte chunk a lane writes in each step
+                const uint32_t rot = (lane >> 1) & 3;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  rows_bias_relu(r == 0 ? raw0 : raw1, s_bias, p.relu, v);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint32_t c = (static_cast<uint32_t>(j) + rot) & 3;
+                    const uint32_t a0 = c == 0 ? pk[0] : (c == 1 ? pk[4] : (c == 2 ? pk[8] : pk[12]));
+                    const uint32_t a1 = c == 0 ? pk[1] : (c == 1 ? pk[5] : (c == 2 ? pk[9] : pk[13]));
+                    const uint32_t a2 = c == 0 ? pk[2] : (c == 1 ? pk[6] : (c == 2 ? pk[10] : pk[14]));
+                    const uint32_t a3 = c == 0 ? pk[3] : (c == 1 ? pk[7] : (c == 2 ? pk[11] : pk[15]));
+                    sts128(row0 + r * 32 * 64 + (c << 4), a0, a1, a2, a3);
+                  }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !(p.dbg & 16)) {
+                  __nv_bfloat16* g = p.out + ((static_cast<size_t>(sg.n) * p.H + y) * p.W + xw) * 32;
+                  bulk_store_1d(g, stage, 32 * 64);
+                  bulk_store_1d(g + static_cast<size_t>(p.W) * 32, stage + 32 * 64, 32 * 64);
+                  bulk_commit();
+                }
+                continue;
+              }
+            }
             // ---- row y
             rows_bias_relu(raw0, s_bias + b * 32, p.relu, v);
             if constexpr (EPI == EPI_POOL_SKIP) {

@@ -471,7 +471,8 @@ struct scv_engine {
   int opt_watchdog_ms = 2000;
   int opt_host_super_tiles = 0;    // ... when the scene streams in from host memory (H2D / compute / D2H overlap);
                                    // 0 = one device batch per K1 / K4 launch: compute starts after ~3 tile rows of H2D
-  int opt_host_register = 1;       // page-lock pageable caller buffers for the duration of a host-buffer mosaic call
+  int opt_host_register = 0;       // page-lock pageable caller buffers for the duration of a host-buffer mosaic call
+                                   // (measured: cudaHostRegister of a scene's 2.4 GB costs 1.3 s, staged copies 0.4 s -> off)
   int opt_super_tiles = 2048;  // target tiles per K1 / K4 launch (a full 10980^2 scene = 1764 chips: x0 4.2 GB + logits 1.0 GB)
   // timing
   std::vector<cudaEvent_t> ev_pool;
@@ -915,6 +916,8 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
         p.pool_pitch = a.bufs[l.pool_buf].channels;
       }
     }
+    if (Ln.slab == 2 && l.epi == EPI_STORE && l.cout == 32 && p.out_pitch == 32 && p.out_choff == 0 && env_int("SCV_LINEAR_STORE", 1))
+      p.linear_out = 1;
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
       fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,
@@ -1380,6 +1383,7 @@ int scv_engine_create(const scv_config* cfg, scv_engine** out) {
   SCV_TRY(build_arch(cfg, &e->arch));
   if (e->arch.cfg.max_batch <= 0) e->arch.cfg.max_batch = 64;
   e->device = cfg->device;
+  e->opt_host_register = env_int("SCV_HOST_REGISTER", 0);
   CUDA_TRY(conv_init_attributes());
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
@@ -1606,6 +1610,15 @@ static void maybe_register(scv_engine* e, scv_engine::Slot& sl, const void* p, s
     cudaGetLastError();  // not fatal: the copies fall back to staged transfers
 }
 
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 // Blocks until the scene that last used `sl` is complete in host memory, then releases its host registrations.
 static int slot_wait(scv_engine* e, scv_engine::Slot& sl) {
   if (!sl.busy) return SCV_OK;
@@ -1670,11 +1683,14 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
 
   // H2D: one chunk per tile row = the mosaic rows it adds to what the rows above already brought (the first
   // chunk also carries the top buffer); a chunk's rows that only this tile row reads are narrowed to its chip
-  // columns, the rows it shares with the next tile row to the union of both.  All chunks are enqueued up front
-  // on the copy stream so PCIe runs back to back while compute starts on chunk 0.
+  // columns, the rows it shares with the next tile row to the union of both.  With page-locked buffers all
+  // chunks are enqueued up front on the copy stream, so PCIe runs back to back while compute starts on chunk 0;
+  // with pageable buffers (every cudaMemcpyAsync is then a blocking staged copy) a chunk is uploaded just before
+  // the first super-batch that needs it, and the download of super-batch k is issued after the kernels of k+1,
+  // so the host blocks in copies while the GPU computes.
   const int ntr = g.r_last - g.r_first + 1;
-  int uploaded = src_row0;
-  for (int r = g.r_first; r <= g.r_last && rc == SCV_OK; ++r) {
+  int uploaded = src_row0, rows_uploaded = 0;
+  auto upload_tile_row = [&](int r) {
     const int need = g.ys[r] - g.half + g.side;  // exclusive
     const int share = r < g.r_last ? std::max(uploaded, g.ys[r + 1] - g.half) : need;  // rows >= share are also read by r+1
     auto copy_rows = [&](int y0, int y1, int xa, int xb) {
@@ -1697,7 +1713,11 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
     cudaEvent_t ev = slot_event(sl.up_ev, r - g.r_first);
     if (!ev) rc = fail(SCV_ERR_CUDA, "cudaEventCreate failed");
     else HOST_TRY(cudaEventRecord(ev, e->h2d));
-  }
+  };
+  const bool pinned_in = host_is_pinned((const uint8_t*)hwc + (size_t)src_row0 * row_bytes);
+  const bool pinned_out = host_is_pinned((uint8_t*)out_prob + (size_t)dst_row0 * W * osz);
+  if (pinned_in && (!acc || pinned_out))
+    for (; rows_uploaded < ntr && rc == SCV_OK; ++rows_uploaded) upload_tile_row(g.r_first + rows_uploaded);
 
   TileJob job{};
   fill_mosaic_job(&job, g, dtype, W, C, norm, opts, force_scalar, e->d_origins);
@@ -1714,39 +1734,47 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
   const int host_super = e->opt_host_super_tiles > 0 ? e->opt_host_super_tiles : e->arch.cfg.max_batch;
   super_batches(g.n(), e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &supers);
   int t0 = 0, rows_downloaded = 0, rows_waited = 0, n_row_ev = 0;
+  // D2H of tile rows [rows_downloaded, upto) (cores only), ordered after `ev` on the compute stream
+  auto download_rows = [&](int upto, cudaEvent_t ev) {
+    if (upto <= rows_downloaded) return;
+    HOST_TRY(cudaStreamWaitEvent(e->d2h, ev, 0));
+    for (int rr = rows_downloaded; rr < upto && rc == SCV_OK; ++rr) {
+      const int r = g.r_first + rr;
+      const size_t xo = (size_t)g.xs[g.c0(r)], wpx = (size_t)(g.c1(r) - g.c0(r)) * K;
+      const size_t doff = (size_t)(g.ys[r] - dst_row0) * W + xo, hoff = (size_t)g.ys[r] * W + xo;
+      HOST_TRY(cudaMemcpy2DAsync((uint8_t*)out_prob + hoff * osz, (size_t)W * osz, (uint8_t*)sl.d_prob + doff * osz,
+                                 (size_t)W * osz, wpx * osz, K, cudaMemcpyDeviceToHost, e->d2h));
+      if (out_mask)
+        HOST_TRY(cudaMemcpy2DAsync(out_mask + hoff, (size_t)W, sl.d_mask + doff, (size_t)W, wpx, K, cudaMemcpyDeviceToHost,
+                                   e->d2h));
+    }
+    rows_downloaded = upto;
+  };
+  int pending_rows = 0;            // tile rows complete once `pending_ev` has fired, not yet downloaded
+  cudaEvent_t pending_ev = nullptr;
   for (auto& sizes : supers) {
     if (rc != SCV_OK) break;
     int nsup = 0;
     for (int nb : sizes) nsup += nb;
     const int last_tile_row = (g.tb + t0 + nsup - 1) / g.ncols - g.r_first;  // relative tile row this super-batch reaches
+    for (; rows_uploaded <= last_tile_row && rc == SCV_OK; ++rows_uploaded) upload_tile_row(g.r_first + rows_uploaded);
     for (; rows_waited <= last_tile_row && rc == SCV_OK; ++rows_waited)
       HOST_TRY(cudaStreamWaitEvent(e->stream, sl.up_ev[rows_waited], 0));
     if (rc != SCV_OK) break;
     if ((rc = run_super(e, job, t0, sizes, e->stream)) != SCV_OK) break;
     t0 += nsup;
-    // D2H of the tile rows completed so far (cores only)
-    const int complete = (g.tb + t0 == g.te) ? ntr : (g.tb + t0) / g.ncols - g.r_first;
-    if (complete > rows_downloaded) {
-      cudaEvent_t ev = slot_event(sl.row_ev, n_row_ev++);
-      if (!ev) {
-        rc = fail(SCV_ERR_CUDA, "cudaEventCreate failed");
-        break;
-      }
-      HOST_TRY(cudaEventRecord(ev, e->stream));
-      HOST_TRY(cudaStreamWaitEvent(e->d2h, ev, 0));
-      for (int rr = rows_downloaded; rr < complete && rc == SCV_OK; ++rr) {
-        const int r = g.r_first + rr;
-        const size_t xo = (size_t)g.xs[g.c0(r)], wpx = (size_t)(g.c1(r) - g.c0(r)) * K;
-        const size_t doff = (size_t)(g.ys[r] - dst_row0) * W + xo, hoff = (size_t)g.ys[r] * W + xo;
-        HOST_TRY(cudaMemcpy2DAsync((uint8_t*)out_prob + hoff * osz, (size_t)W * osz, (uint8_t*)sl.d_prob + doff * osz,
-                                   (size_t)W * osz, wpx * osz, K, cudaMemcpyDeviceToHost, e->d2h));
-        if (out_mask)
-          HOST_TRY(cudaMemcpy2DAsync(out_mask + hoff, (size_t)W, sl.d_mask + doff, (size_t)W, wpx, K, cudaMemcpyDeviceToHost,
-                                     e->d2h));
-      }
-      rows_downloaded = complete;
+    cudaEvent_t ev = slot_event(sl.row_ev, n_row_ev++);
+    if (!ev) {
+      rc = fail(SCV_ERR_CUDA, "cudaEventCreate failed");
+      break;
     }
+    HOST_TRY(cudaEventRecord(ev, e->stream));
+    // the previous super-batch's rows leave now: its kernels are done or running, this one's are queued behind
+    if (pending_ev) download_rows(pending_rows, pending_ev);
+    pending_rows = (g.tb + t0 == g.te) ? ntr : (g.tb + t0) / g.ncols - g.r_first;
+    pending_ev = ev;
   }
+  if (rc == SCV_OK && pending_ev) download_rows(pending_rows, pending_ev);
 #undef HOST_TRY
   sl.busy = true;
   cudaEventRecord(sl.compute_done, e->stream);

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractParams p) {
 // No shared memory, no block barrier: ~45 instructions per pixel instead of ~110, and every byte of a 128-byte
 // line is consumed by the same warp within three consecutive instructions (L1 hits).
 template <bool SUB>
-__global__ void __launch_bounds__(256) extract_u16x6_kernel(const ExtractParams p) {
+__global__ void __launch_bounds__(256, 8) extract_u16x6_kernel(const ExtractParams p) {
   int tile, r0;
   if (!extract_block_unit(p, 8, tile, r0)) return;
   const int row = r0 + (threadIdx.x >> 5);
@@ -413,10 +413,16 @@ __global__ void __launch_bounds__(256) tile_stats_kernel(const TileStatsParams p
   }
 }
 
+// sigmoid with the hardware exp2 / reciprocal approximations (relative error ~1e-6, far inside the 1e-2 budget):
+// the full-precision expf + IEEE division made K4 ALU-bound under the power-capped clocks of a long step (ncu:
+// sm__throughput 73 % next to 60 % DRAM).  Every head path uses this one function, so stitched rasters and
+// whole-tile predictions stay bit-identical.
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
 __device__ __forceinline__ void head_eval(const float* z, int ncls, int head, float thr, int out_channel,
                                           float& prob, int& cls) {
   if (head == SCV_HEAD_SIGMOID) {
-    const float pr = 1.f / (1.f + expf(-z[0]));
+    const float pr = sigmoid_fast(z[0]);
     prob = pr;
     cls = pr > thr ? 1 : 0;
   } else {
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(256) stitch_kernel_vec(const StitchParams p) {
     z[4 * k] = t.x, z[4 * k + 1] = t.y, z[4 * k + 2] = t.z, z[4 * k + 3] = t.w;
   }
 #pragma unroll
-  for (int k = 0; k < PX; ++k) pr[k] = 1.f / (1.f + expf(-z[k]));
+  for (int k = 0; k < PX; ++k) pr[k] = sigmoid_fast(z[k]);
   const size_t o = static_cast<size_t>(d.y + row - p.dst_row0) * p.out_W + d.x + col;
   if (p.prob) {
     if constexpr (sizeof(OUT) == 4) {
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(256) head_tiles_kernel(const HeadTilesParams p
   float zz[SCV_MAX_CLASSES];
   for (int k = 0; k < p.ncls; ++k) zz[k] = __ldg(p.logits + i * p.ncls + k);
   if (p.head == SCV_HEAD_SIGMOID) {
-    const float pr = 1.f / (1.f + expf(-zz[0]));
+    const float pr = sigmoid_fast(zz[0]);
     if (p.probs) p.probs[i] = pr;
     if (p.classes) p.classes[i] = pr > p.threshold ? 1 : 0;
   } else {

@@ -113,7 +113,7 @@ def test_bench_scene_slice_matches_oracle():
     import bench
     H, W = 64 + 256 + 192 + 1, bench.SCENE
     scene = bench.make_scene(H, W, seed=1)
-    m = model_tools.binary_unet(nchannels=6, max_batch=126, outputs='probs')
+    m = model_tools.binary_unet(nchannels=6, max_batch=126, outputs='probs', seed=0)   # as bench.py builds it
     w = bench.random_weights(m, seed=0)
     m.set_weights(w)
     spec = processing.rescale_spec(6, moments=[(0, 10000)] * 6)
