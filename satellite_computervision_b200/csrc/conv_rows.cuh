@@ -469,43 +469,35 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             t_zero += ROWS_CLOCK() - tl1;
             if (p.dbg & 1) continue;
             const long long ts0 = ROWS_CLOCK();
-            if (lane == 0) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
+            // Two ways out of the staging tile.  TMA (default): swizzled rows, one tensor-map store per tile.
+            // LSU (p.linear_out, experiment): LINEAR rows (a lane rotates which 16-byte chunk it writes per step, so the
+            // shared-memory stores stay conflict free), read back 512 contiguous bytes per warp instruction and written
+            // with ordinary coalesced 128-bit stores.  Both cost the same on the 384 x 384 layers (~11.5 B/clk per SM
+            // of output whatever the path, profiles/r02_store_path.md), so the store path is not the limiter.
+            const bool lsu = p.linear_out != 0;
+            if (!lsu && lane == 0) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
             __syncwarp();
             t_st += ROWS_CLOCK() - ts0;
             const uint32_t row0 = smem_u32(stage) + lane * 64;
             float v[32];
             uint32_t pk[16], w0[16];
-            if constexpr (EPI == EPI_STORE && COUT == 32) {
-              if (p.linear_out) {
-                // dense output: LINEAR staging (pixel-major, 64 B per pixel) and one plain 2 KB bulk store per
-                // row; bank conflicts are avoided by rotating which 16-byte chunk a lane writes in each step
-                const uint32_t rot = (lane >> 1) & 3;
+            auto put = [&](uint32_t rowaddr, const uint32_t (&qv)[16], uint32_t key) {
+              if (lsu) {
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  rows_bias_relu(r == 0 ? raw0 : raw1, s_bias, p.relu, v);
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const uint32_t c = (static_cast<uint32_t>(j) + rot) & 3;
-                    const uint32_t a0 = c == 0 ? pk[0] : (c == 1 ? pk[4] : (c == 2 ? pk[8] : pk[12]));
-                    const uint32_t a1 = c == 0 ? pk[1] : (c == 1 ? pk[5] : (c == 2 ? pk[9] : pk[13]));
-                    const uint32_t a2 = c == 0 ? pk[2] : (c == 1 ? pk[6] : (c == 2 ? pk[10] : pk[14]));
-                    const uint32_t a3 = c == 0 ? pk[3] : (c == 1 ? pk[7] : (c == 2 ? pk[11] : pk[15]));
-                    sts128(row0 + r * 32 * 64 + (c << 4), a0, a1, a2, a3);
-                  }
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t c = (static_cast<uint32_t>(j) + key) & 3;
+                  const uint32_t a0 = c == 0 ? qv[0] : (c == 1 ? qv[4] : (c == 2 ? qv[8] : qv[12]));
+                  const uint32_t a1 = c == 0 ? qv[1] : (c == 1 ? qv[5] : (c == 2 ? qv[9] : qv[13]));
+                  const uint32_t a2 = c == 0 ? qv[2] : (c == 1 ? qv[6] : (c == 2 ? qv[10] : qv[14]));
+                  const uint32_t a3 = c == 0 ? qv[3] : (c == 1 ? qv[7] : (c == 2 ? qv[11] : qv[15]));
+                  sts128(rowaddr + (c << 4), a0, a1, a2, a3);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0 && !(p.dbg & 16)) {
-                  __nv_bfloat16* g = p.out + ((static_cast<size_t>(sg.n) * p.H + y) * p.W + xw) * 32;
-                  bulk_store_1d(g, stage, 32 * 64);
-                  bulk_store_1d(g + static_cast<size_t>(p.W) * 32, stage + 32 * 64, 32 * 64);
-                  bulk_commit();
-                }
-                continue;
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts128(rowaddr + ((static_cast<uint32_t>(j) ^ key) << 4), qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
               }
-            }
+            };
             // ---- row y
             rows_bias_relu(raw0, s_bias + b * 32, p.relu, v);
             if constexpr (EPI == EPI_POOL_SKIP) {
@@ -515,9 +507,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128(row0 + ((static_cast<uint32_t>(j) ^ phase) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            put(row0, pk, phase);  // (lane >> 1) & 3: SWIZZLE_64B phase of the row == a conflict-free rotation
             // ---- row y+1
             rows_bias_relu(raw1, s_bias + b * 32, p.relu, v);
             if constexpr (EPI == EPI_POOL_SKIP) {
@@ -529,28 +519,53 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
               }
               if (!(lane & 1)) {
                 const uint32_t pp = lane >> 1;  // pooled pixel of this warp
-                const uint32_t prow = smem_u32(stage) + 2 * 32 * 64 + pp * 64;
-                const uint32_t pph = (pp >> 1) & 3;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  sts128(prow + ((static_cast<uint32_t>(j) ^ pph) << 4), w0[4 * j], w0[4 * j + 1], w0[4 * j + 2], w0[4 * j + 3]);
+                put(smem_u32(stage) + 2 * 32 * 64 + pp * 64, w0, (pp >> 1) & 3);
               }
               rows_skip_affine(s_extra + b * 32, s_extra + COUT + b * 32, v);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(j) ^ phase) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            put(row0 + 32 * 64, pk, phase);
             const long long tf0 = ROWS_CLOCK();
-            fence_proxy_async();
-            __syncwarp();
-            t_fence += ROWS_CLOCK() - tf0;
-            if (lane == 0 && !(p.dbg & 16)) {
-              if (p.out != nullptr) tma_store_4d(&tmOut, stage, p.out_choff + b * 32, xw, y, sg.n);
-              if constexpr (EPI == EPI_POOL_SKIP) tma_store_4d(&tmPool, stage + 2 * 32 * 64, b * 32, xw >> 1, y >> 1, sg.n);
-              bulk_commit();
+            if (lsu) {
+              __syncwarp();
+              if (!(p.dbg & 16)) {
+                const uint32_t sub = lane >> 2, c16 = (lane & 3) * 16;  // pixel within a group of 8, 16-byte chunk of its 64 B
+                if (p.out != nullptr) {
+#pragma unroll
+                  for (int r = 0; r < 2; ++r) {
+                    uint8_t* g = reinterpret_cast<uint8_t*>(p.out) +
+                                 (((static_cast<size_t>(sg.n) * p.H + y + r) * p.W + xw + sub) * p.out_pitch + p.out_choff + b * 32) * 2 + c16;
+                    const size_t px8 = static_cast<size_t>(8) * p.out_pitch * 2;
+                    uint4 t[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) t[k] = lds128(smem_u32(stage) + r * 2048 + k * 512 + lane * 16);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(g + k * px8) = t[k];
+                  }
+                }
+                if constexpr (EPI == EPI_POOL_SKIP) {
+                  uint8_t* g = reinterpret_cast<uint8_t*>(p.pool_out) +
+                               (((static_cast<size_t>(sg.n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (xw >> 1) + sub) * p.pool_pitch + b * 32) * 2 + c16;
+                  const size_t px8 = static_cast<size_t>(8) * p.pool_pitch * 2;
+                  uint4 t[2];
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) t[k] = lds128(smem_u32(stage) + 4096 + k * 512 + lane * 16);
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(g + k * px8) = t[k];
+                }
+              }
+              // (the __syncwarp at the top of the next block orders these reads before the next staging writes)
+            } else {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0 && !(p.dbg & 16)) {
+                if (p.out != nullptr) tma_store_4d(&tmOut, stage, p.out_choff + b * 32, xw, y, sg.n);
+                if constexpr (EPI == EPI_POOL_SKIP) tma_store_4d(&tmPool, stage + 2 * 32 * 64, b * 32, xw >> 1, y >> 1, sg.n);
+                bulk_commit();
+              }
             }
+            t_fence += ROWS_CLOCK() - tf0;
           }
         }
       }

@@ -54,10 +54,8 @@ struct ConvParams {
   int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
   int dbg;              // timing experiments only (env SCV_ROWS_DBG; results are wrong when non-zero)
-  int linear_out;       // row kernel, EPI_STORE: out is a dense tensor (pitch == Cout == 32, no channel offset), so a warp's
-                        // 32 pixels x 32 channels of one row are ONE contiguous 2 KB run -> plain bulk stores.  A tensor-map
-                        // store walks its box in 64-byte rows at ~5.6 cycles each, which alone floors every 32-channel
-                        // 384 x 384 output at 6.2 ms per scene (profiles/r02_tma_store_row_rate.md)
+  int linear_out;       // row kernel, experiment: bf16 outputs leave the staging tile through ordinary coalesced stores
+                        // instead of TMA stores (no faster: see conv_rows.cuh)
   // watchdog
   int* err;
   unsigned long long watchdog_ns;

@@ -916,7 +916,10 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
         p.pool_pitch = a.bufs[l.pool_buf].channels;
       }
     }
-    if (Ln.slab == 2 && l.epi == EPI_STORE && l.cout == 32 && p.out_pitch == 32 && p.out_choff == 0 && env_int("SCV_LINEAR_STORE", 1))
+    // experiment switch (off): row-kernel outputs through ordinary stores instead of TMA stores.  Measured equal for
+    // EPI_STORE and slower for the pooling epilogue (profiles/r02_store_path.md): the store PATH is not what bounds
+    // the 384 x 384 layers.
+    if (Ln.slab == 2 && (l.epi == EPI_STORE || l.epi == EPI_POOL_SKIP) && env_int("SCV_LSU_STORE", 0))
       p.linear_out = 1;
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))

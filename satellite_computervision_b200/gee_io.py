@@ -304,8 +304,18 @@ def iter_patches(file_list, features, kernel_shape=(256, 256), kernel_buffer=(12
                 dic[k] = v.reshape(h, w)
             bands = np.stack([dic[k] for k in features if k not in one_hot], axis=-1)
             extra = [np.asarray(fxn(dic), np.float32)[..., None] for fxn in (derived or {}).values()]
-            hot = [np.eye(depth, dtype=np.float32)[dic[k].astype(np.uint8)] for k, depth in one_hot.items()]
+            hot = [_one_hot(dic[k].astype(np.uint8), depth) for k, depth in one_hot.items()]
             yield bands, extra, hot
+
+
+def _one_hot(idx, depth):
+    """``tf.one_hot(tf.cast(x, tf.uint8), depth)`` (``utils/prediction_tools.py:198-200``): a category outside
+    [0, depth) yields an all-zero vector instead of an error."""
+    idx = np.asarray(idx).astype(np.int64)
+    out = np.zeros(idx.shape + (int(depth),), dtype=np.float32)
+    ok = (idx >= 0) & (idx < depth)
+    np.put_along_axis(out, np.where(ok, idx, 0)[..., None], ok[..., None].astype(np.float32), axis=-1)
+    return out
 
 
 def write_patch_tfrecords(path, patches, features, compression='GZIP'):

@@ -481,11 +481,70 @@ def _layer_kind(name):
     return None
 
 
+def _match_structural(by_layer, model, path):
+    """Keras 3 file of the reference's own ``get_unet_model`` (subclassed blocks, ``utils/model_tools.py:174-286``):
+    encoder_i / conv_block groups hold nested ``encoder/cba1/{conv_layer,bn_layer}`` sub-layers, the decoder is
+    functional (auto-named conv2d_transpose / batch_normalization / conv2d, head ``probs`` / ``logits``).  Returns the
+    tensors in the model's ``get_weights()`` order or raises: file order is NOT get_weights() order, so there is no
+    positional fallback."""
+    paths = list(by_layer)
+
+    def nested(top_pred, tail):
+        hits = [p for p in paths if top_pred(p.split('/', 1)[0]) and p.endswith(tail)]
+        return hits[0] if len(hits) == 1 else None
+
+    flat = {}
+    for p in paths:
+        k = _layer_kind(p)
+        if k is not None:
+            flat.setdefault(k, []).append(p)
+    for v in flat.values():
+        v.sort(key=_natural)
+    heads = [p for p in paths if p in ('probs', 'logits') or p.endswith('probs')]
+    ordered, used = [], set()
+    prefixes = []
+    for name in model.weight_names:
+        pre = name.rsplit('/', 1)[0]
+        if not prefixes or prefixes[-1] != pre:
+            prefixes.append(pre)
+    for pre in prefixes:
+        block, _, leaf = pre.partition('/')
+        hit = None
+        if block.startswith('encoder_') or block == 'center':
+            j = int(leaf[-1]) + 1
+            tail = f'cba{j}/' + ('bn_layer' if leaf.startswith('bn') else 'conv_layer')
+            if block == 'center':
+                hit = nested(lambda t: t.startswith('conv_block'), tail)
+            else:
+                i = block.split('_')[1]
+                hit = nested(lambda t: t in (f'encoder_{i}', 'encoder_block' if i == '0' else f'encoder_block_{i}'), tail)
+        elif pre == 'head':
+            hit = heads[0] if len(heads) == 1 else (flat.get('conv2d') or [None])[-1]
+            if hit in flat.get('conv2d', []):
+                flat['conv2d'].remove(hit)
+        else:
+            kind = 'conv2d_transpose' if leaf == 'up' else ('batch_normalization' if leaf.startswith('bn') else 'conv2d')
+            cands = flat.get(kind, [])
+            if kind == 'conv2d' and len(heads) != 1 and len(cands) == 1:
+                cands = []  # the last auto-named conv2d is the head
+            hit = cands.pop(0) if cands else None
+        if hit is None or hit in used:
+            raise ValueError(f'{path}: cannot find the Keras layer for {pre!r} among {sorted(paths)[:6]}... '
+                             '(expected auto-named functional layers or the reference\'s nested encoder_i/encoder/cbaN groups)')
+        used.add(hit)
+        ordered += by_layer[hit]
+    if len(used) != len(paths):
+        raise ValueError(f'{path}: {len(paths) - len(used)} layer group(s) of the file were not matched: '
+                         f'{sorted(set(paths) - used)[:6]}')
+    return ordered
+
+
 def read_weights(path, model=None):
     """Flat float32 weight list for ``UNetModel.set_weights``.  Legacy files are already in
     ``get_weights()`` order.  Keras 3 files are keyed by layer name only, so with a ``model`` the layers are
     matched by kind in creation order (conv2d, conv2d_1, ... / batch_normalization... / conv2d_transpose...),
-    the way a functional U-Net numbers them; other names keep their file order."""
+    the way a functional U-Net numbers them, or -- for files written from the reference's own
+    subclassed blocks -- by their nested structure; anything else is an error, never a positional guess."""
     named = read_named_weights(path)
     keras3 = bool(named) and '/vars/' in named[0][0]
     if keras3 and model is not None:
@@ -494,7 +553,7 @@ def read_weights(path, model=None):
             by_layer.setdefault(n.split('/vars/')[0], []).append(wgt)
         kinds = {}
         for lname in by_layer:
-            k = _layer_kind(lname.rsplit('/', 1)[-1])
+            k = _layer_kind(lname.rsplit('/', 1)[-1]) if '/' not in lname else None
             if k is not None:
                 kinds.setdefault(k, []).append(lname)
         if sum(len(v) for v in kinds.values()) == len(by_layer):
@@ -506,7 +565,9 @@ def read_weights(path, model=None):
                 if not kinds.get(k):
                     raise ValueError(f'{path}: no {k} layer left for {lname}')
                 ordered += by_layer[kinds[k].pop(0)]
-            named = [('', wgt) for wgt in ordered]
+        else:
+            ordered = _match_structural(by_layer, model, path)
+        named = [('', wgt) for wgt in ordered]
     ws = [np.ascontiguousarray(w, dtype=np.float32) for _, w in named]
     if model is not None and len(ws) != len(model.weight_shapes):
         raise ValueError(f'{path}: file holds {len(ws)} weight tensors, the model expects {len(model.weight_shapes)}')
@@ -701,13 +762,20 @@ def keras_layer_groups(model):
 
 
 def write_weights_keras3(path, layers):
-    """Keras 3 ``.weights.h5`` layout: ``layers/<layer>/vars/<i>`` (used by the tests)."""
+    """Keras 3 ``.weights.h5`` layout: ``layers/<layer>[/<sub-layer>...]/vars/<i>`` (used by the tests); a layer name
+    containing '/' becomes nested groups, the way sub-layers of a subclassed layer are stored."""
     w = _Writer()
-    links = {}
+    tree = {}
     for lname, weights in layers:
-        vars_g = w.group({str(i): w.dataset(np.asarray(a, np.float32)) for i, (_, a) in enumerate(weights)})[0]
-        links[lname] = w.group({'vars': vars_g})[0]
-    root = w.group({'layers': w.group(links)[0], 'vars': w.group({})[0]})
+        node = tree
+        for part in lname.split('/'):
+            node = node.setdefault(part, {})
+        node['vars'] = w.group({str(i): w.dataset(np.asarray(a, np.float32)) for i, (_, a) in enumerate(weights)})[0]
+
+    def emit(node):
+        return w.group({k: (v if k == 'vars' else emit(v)) for k, v in node.items()})[0]
+
+    root = w.group({'layers': emit(tree), 'vars': w.group({})[0]})
     with open(path, 'wb') as fh:
         fh.write(w.finish(root))
     return path

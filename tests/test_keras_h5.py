@@ -139,6 +139,31 @@ def test_model_weight_grouping_round_trip(tmp_path):
         kh.read_weights(p, short)
 
 
+def test_keras3_nested_reference_blocks_are_matched_by_structure(tmp_path):
+    """ADVICE: a Keras 3 file saved from the reference's own get_unet_model has nested encoder_i/encoder/cbaN/
+    {conv_layer,bn_layer} groups (utils/model_tools.py:174-286) next to the auto-named functional decoder; the file
+    order (alphabetical) is not get_weights() order, so tensors are matched by structure -- or the load fails."""
+    m = _unet_like(np.random.default_rng(5))
+    w = dict(zip(m.weight_names, m.get_weights()))
+
+    def take(prefix, leaves):
+        return [(f'{prefix}/{l}', w[f'{prefix}/{l}']) for l in leaves]
+    cv, bnl = ['kernel', 'bias'], ['gamma', 'beta', 'moving_mean', 'moving_variance']
+    layers = [('encoder_0/encoder/cba1/conv_layer', take('encoder_0/conv0', cv)), ('encoder_0/encoder/cba1/bn_layer', take('encoder_0/bn0', bnl)),
+              ('encoder_0/encoder/cba2/conv_layer', take('encoder_0/conv1', cv)), ('encoder_0/encoder/cba2/bn_layer', take('encoder_0/bn1', bnl)),
+              ('conv_block/cba1/conv_layer', take('center/conv0', cv)), ('conv_block/cba1/bn_layer', take('center/bn0', bnl)),
+              ('conv2d_transpose', take('decoder_0/up', cv)), ('batch_normalization', take('decoder_0/bn_cat', bnl)),
+              ('conv2d', take('decoder_0/conv0', cv)), ('batch_normalization_1', take('decoder_0/bn0', bnl)),
+              ('probs', take('head', cv))]
+    p = kh.write_weights_keras3(str(tmp_path / 'ref.weights.h5'), layers)
+    got = kh.read_weights(p, m)
+    assert len(got) == len(m.get_weights()) and all(np.array_equal(a, b) for a, b in zip(got, m.get_weights()))
+    # an unknown layer group is an error, not a positional guess
+    bad = kh.write_weights_keras3(str(tmp_path / 'bad.weights.h5'), layers[:-1] + [('my_custom_head', take('head', cv))])
+    with pytest.raises(ValueError, match='cannot find the Keras layer|not matched'):
+        kh.read_weights(bad, m)
+
+
 def test_new_style_container_hand_assembled():
     """Superblock v2, 'OHDR' v2 object headers, compact groups made of link messages, v2 dataspaces, a v3
     attribute holding a variable-length UTF-8 string in a global heap -- assembled byte by byte here,
