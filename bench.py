@@ -391,6 +391,7 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
     clk.__exit__(None, None, None)
+    times_e2e = model.times()
     rects = sharding.shard_rects(sh, H, W, BUFF)
     h2d = (src_row1 - src_row0) * W * BANDS * 2  # upper bound: partial first / last tile rows copy fewer columns
     d2h = sum((y1 - y0) * (x1 - x0) for y0, y1, x0, x1 in rects) * 5
@@ -474,7 +475,9 @@ def main():
                        'scene_megapixels': mp_scene, 'chips_rank0': n_my,
                        'l2': 'inputs larger than L2 (scene shard 1.43 GB/N, activations > 126 MB per batch); no explicit flush'},
             'e2e': {'value': mp_scene / (e2e_ms / 1e3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
-                    'd2h_bytes_per_step': d2h},
+                    'd2h_bytes_per_step': d2h,
+                    'pipeline_ms_last_step_rank0': {'h2d_lead': times_e2e['h2d_lead_ms'], 'kernels': times_e2e['total_ms'],
+                                                    'd2h_tail': times_e2e['d2h_tail_ms']}},
             'gpu_launches': int(times['n_launches']) * args.steps,  # rank 0's kernels in the timed device-resident region
             'clocks': clk.summary(),
             'roofline': {'bound': 'tensor', 'kernel': 'tcgen05 implicit-GEMM conv kernels (all 27 conv/convT layers of the U-Net)',

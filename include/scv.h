@@ -155,6 +155,9 @@ typedef struct {
   float layer_ms[SCV_MAX_LAYERS];   /* per layer, summed over batches (only when
                                        scv_set_option("profile_layers",1))      */
   double layer_flops[SCV_MAX_LAYERS]; /* algorithmic FLOPs per tile of that layer */
+  /* host-buffer mosaic calls only (0 otherwise): the exposed ends of the H2D / compute / D2H pipeline */
+  float h2d_lead_ms;                /* first H2D copy enqueued -> first kernel starts */
+  float d2h_tail_ms;                /* last kernel ends -> last D2H copy lands        */
 } scv_times;
 
 /* ---- lifecycle ------------------------------------------------------------ */

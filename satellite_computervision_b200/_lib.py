@@ -60,7 +60,7 @@ class Times(C.Structure):
     _fields_ = [('total_ms', C.c_float), ('extract_ms', C.c_float), ('network_ms', C.c_float),
                 ('stitch_ms', C.c_float), ('n_batches', C.c_int), ('n_tiles', C.c_int), ('n_launches', C.c_int),
                 ('n_layers', C.c_int), ('layer_ms', C.c_float * SCV_MAX_LAYERS),
-                ('layer_flops', C.c_double * SCV_MAX_LAYERS)]
+                ('layer_flops', C.c_double * SCV_MAX_LAYERS), ('h2d_lead_ms', C.c_float), ('d2h_tail_ms', C.c_float)]
 
 
 # every symbol include/scv.h declares: name -> (restype, argtypes)

@@ -471,6 +471,7 @@ struct scv_engine {
   int opt_watchdog_ms = 2000;
   int opt_host_super_tiles = 0;    // ... when the scene streams in from host memory (H2D / compute / D2H overlap);
                                    // 0 = one device batch per K1 / K4 launch: compute starts after ~3 tile rows of H2D
+  int opt_host_first_row = 1;      // host-buffer mosaic calls: first super-batch = first tile row (short pipeline start)
   int opt_host_register = 0;       // page-lock pageable caller buffers for the duration of a host-buffer mosaic call
                                    // (measured: cudaHostRegister of a scene's 2.4 GB costs 1.3 s, staged copies 0.4 s -> off)
   int opt_super_tiles = 2048;  // target tiles per K1 / K4 launch (a full 10980^2 scene = 1764 chips: x0 4.2 GB + logits 1.0 GB)
@@ -483,6 +484,7 @@ struct scv_engine {
   };
   std::vector<BatchEv> batch_ev;
   int n_launches = 0;
+  int ev_host_begin = -1, ev_host_end = -1;  // host-buffer calls: first H2D enqueued (copy stream) / last D2H landed
   int last_side = 0;
   bool times_pending = false;
   scv_times times{};
@@ -948,6 +950,7 @@ static void reset_timing(scv_engine* e) {
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   e->ev_pool.clear();
   e->batch_ev.clear();
+  e->ev_host_begin = e->ev_host_end = -1;
   e->n_launches = 0;
   e->times_pending = false;
 }
@@ -1001,6 +1004,11 @@ static int finalize_times(scv_engine* e) {
         }
     }
     t.n_batches = (int)e->batch_ev.size();
+    if (e->ev_host_begin >= 0 && e->ev_host_end >= 0) {
+      CUDA_TRY(cudaEventSynchronize(e->ev_pool[e->ev_host_end]));
+      cudaEventElapsedTime(&t.h2d_lead_ms, e->ev_pool[e->ev_host_begin], e->ev_pool[e->batch_ev.front().e0]);
+      cudaEventElapsedTime(&t.d2h_tail_ms, e->ev_pool[e->batch_ev.back().e3], e->ev_pool[e->ev_host_end]);
+    }
   }
   t.n_launches = e->n_launches;
   e->times_pending = false;
@@ -1387,6 +1395,7 @@ int scv_engine_create(const scv_config* cfg, scv_engine** out) {
   if (e->arch.cfg.max_batch <= 0) e->arch.cfg.max_batch = 64;
   e->device = cfg->device;
   e->opt_host_register = env_int("SCV_HOST_REGISTER", 0);
+  e->opt_host_first_row = env_int("SCV_HOST_FIRST_ROW", 1);
   CUDA_TRY(conv_init_attributes());
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
@@ -1486,6 +1495,7 @@ int scv_set_option(scv_engine* e, const char* key, int value) {
   else if (k == "super_tiles") e->opt_super_tiles = std::max(1, value);
   else if (k == "host_super_tiles") e->opt_host_super_tiles = std::max(0, value);
   else if (k == "host_register") e->opt_host_register = value;
+  else if (k == "host_first_row") e->opt_host_first_row = value;
   else return fail(SCV_ERR_INVALID, "unknown option '%s'", key);
   return SCV_OK;
 }
@@ -1693,6 +1703,7 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
   // so the host blocks in copies while the GPU computes.
   const int ntr = g.r_last - g.r_first + 1;
   int uploaded = src_row0, rows_uploaded = 0;
+  e->ev_host_begin = new_event(e, e->h2d);
   auto upload_tile_row = [&](int r) {
     const int need = g.ys[r] - g.half + g.side;  // exclusive
     const int share = r < g.r_last ? std::max(uploaded, g.ys[r + 1] - g.half) : need;  // rows >= share are also read by r+1
@@ -1735,7 +1746,16 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
   // of H2D and the D2H tail after the last K4 stays short.
   std::vector<std::vector<int>> supers;
   const int host_super = e->opt_host_super_tiles > 0 ? e->opt_host_super_tiles : e->arch.cfg.max_batch;
-  super_batches(g.n(), e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &supers);
+  {
+    // the first super-batch is the (rest of the) first tile row only: the kernels start after ONE tile row of H2D
+    // instead of the three a full device batch spans, and the exposed start of the pipeline shrinks accordingly
+    const int first = e->opt_host_first_row ? std::min({g.n(), g.ncols - g.c0(g.r_first), e->arch.cfg.max_batch}) : 0;
+    std::vector<std::vector<int>> rest;
+    super_batches(g.n() - first, e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &rest);
+    if (first > 0 && g.n() - first >= e->arch.cfg.max_batch / 2) supers.push_back(std::vector<int>{first});
+    else if (first > 0) super_batches(g.n(), e->arch.cfg.max_batch, std::min(e->opt_super_tiles, host_super), &rest);
+    for (auto& r : rest) supers.push_back(r);
+  }
   int t0 = 0, rows_downloaded = 0, rows_waited = 0, n_row_ev = 0;
   // D2H of tile rows [rows_downloaded, upto) (cores only), ordered after `ev` on the compute stream
   auto download_rows = [&](int upto, cudaEvent_t ev) {
@@ -1778,6 +1798,7 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
     pending_ev = ev;
   }
   if (rc == SCV_OK && pending_ev) download_rows(pending_rows, pending_ev);
+  e->ev_host_end = new_event(e, e->d2h);
 #undef HOST_TRY
   sl.busy = true;
   cudaEventRecord(sl.compute_done, e->stream);

@@ -167,7 +167,8 @@ class UNetModel:
         nl = t.n_layers
         return dict(total_ms=t.total_ms, extract_ms=t.extract_ms, network_ms=t.network_ms, stitch_ms=t.stitch_ms,
                     n_batches=t.n_batches, n_tiles=t.n_tiles, n_launches=t.n_launches,
-                    layer_ms=list(t.layer_ms[:nl]), layer_flops=list(t.layer_flops[:nl]))
+                    layer_ms=list(t.layer_ms[:nl]), layer_flops=list(t.layer_flops[:nl]),
+                    h2d_lead_ms=t.h2d_lead_ms, d2h_tail_ms=t.d2h_tail_ms)
 
     def close(self):
         if self._engine is not None:

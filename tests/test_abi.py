@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Tiling) == 8
     assert C.sizeof(_lib.MosaicOpts) == 4 * 9
     assert C.sizeof(_lib.Crop) == 16
-    assert C.sizeof(_lib.Times) == 4 * 4 + 4 * 4 + 64 * 4 + 64 * 8
+    assert C.sizeof(_lib.Times) == 4 * 4 + 4 * 4 + 64 * 4 + 64 * 8 + 8
 
 
 @pytest.mark.parametrize('double_conv,ncls,nch,filters', [(1, 1, 6, [32, 64, 128, 256, 512]), (0, 2, 6, [32, 64, 128, 256, 512]),
