@@ -107,6 +107,8 @@ class ClockSampler:
         self.gpu, self.lines, self.proc = gpu_index, [], None
 
     def __enter__(self):
+        if self.gpu < 0:
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -368,7 +370,7 @@ def main():
         step_device()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk = ClockSampler(local_rank)
+    clk = ClockSampler(local_rank if rank == 0 else -1)  # rank 0's GPU only: eight nvidia-smi pollers contend for the driver
     clk.__enter__()  # sampled over both timed legs (device-resident and end-to-end): short multi-GPU steps still get samples
     ev0.record(stream)
     for _ in range(args.steps):
@@ -389,9 +391,13 @@ def main():
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.synchronize()
-    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_local = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = reduce_max(e2e_local * args.steps) / args.steps
     clk.__exit__(None, None, None)
     times_e2e = model.times()
+    print(f'[rank {rank}] chips {sh.n_chips} device-leg kernels {times["total_ms"]:.2f} ms | e2e {e2e_local:.2f} ms = lead '
+          f'{times_e2e["h2d_lead_ms"]:.2f} + kernels {times_e2e["total_ms"]:.2f} + tail {times_e2e["d2h_tail_ms"]:.2f} + host '
+          f'{e2e_local - times_e2e["h2d_lead_ms"] - times_e2e["total_ms"] - times_e2e["d2h_tail_ms"]:.2f}', file=sys.stderr, flush=True)
     rects = sharding.shard_rects(sh, H, W, BUFF)
     h2d = (src_row1 - src_row0) * W * BANDS * 2  # upper bound: partial first / last tile rows copy fewer columns
     d2h = sum((y1 - y0) * (x1 - x0) for y0, y1, x0, x1 in rects) * 5

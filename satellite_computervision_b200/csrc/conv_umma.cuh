@@ -638,8 +638,8 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
         const uint64_t da0 = umma_smem_desc(a_addr, ROW_BYTES);
         const uint64_t db0 = umma_smem_desc(a_addr + A_BYTES, ROW_BYTES);
         // ---- the turn: stage g may only be issued after stage g-1
-        if (ni > 1) {
-          const uint32_t par = me == 0 ? ((nth & 1) ^ 1) : (nth & 1);
+        if (ni > 1 && !(me == 0 && nth == 0)) {  // issuer 0 starts with the token; its k-th later turn waits for arrival k
+          const uint32_t par = me == 0 ? ((nth - 1) & 1) : (nth & 1);
           const bool ok3 = mbar_wait(&turn[me], par, abort_flag, p.watchdog_ns);
           if (!__all_sync(0xffffffffu, ok3)) {
             run = false;

@@ -477,6 +477,7 @@ struct scv_engine {
   int opt_super_tiles = 2048;  // target tiles per K1 / K4 launch (a full 10980^2 scene = 1764 chips: x0 4.2 GB + logits 1.0 GB)
   // timing
   std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
   struct BatchEv {
     int e0, e1, e2, e3;
     std::vector<int> layer_ev;
@@ -936,19 +937,20 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
   return SCV_OK;
 }
 
+// Timing events are pooled per engine and re-recorded call after call (creating / destroying ~100 events per call
+// showed up as host time at 8 ranks per box).
 static int new_event(scv_engine* e, cudaStream_t s) {
-  static thread_local int dummy;
-  (void)dummy;
-  cudaEvent_t ev;
-  if (cudaEventCreate(&ev) != cudaSuccess) return -1;
-  cudaEventRecord(ev, s);
-  e->ev_pool.push_back(ev);
-  return (int)e->ev_pool.size() - 1;
+  if (e->ev_used == e->ev_pool.size()) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return -1;
+    e->ev_pool.push_back(ev);
+  }
+  cudaEventRecord(e->ev_pool[e->ev_used], s);
+  return (int)e->ev_used++;
 }
 
 static void reset_timing(scv_engine* e) {
-  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
-  e->ev_pool.clear();
+  e->ev_used = 0;
   e->batch_ev.clear();
   e->ev_host_begin = e->ev_host_end = -1;
   e->n_launches = 0;
@@ -1421,6 +1423,7 @@ void scv_engine_destroy(scv_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   reset_timing(e);
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   for (auto& pl : e->plans) cudaFree(pl->arena);
   for (auto& l : e->arch.layers) {
     cudaFree(l.d_w);
