@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  grid_dep_launch();  // programmatic dependent launch: see launch_pdl()
+  grid_dep_wait();    // nothing above reads an activation; everything below may
 
   if (warp == 0) {
     // ===================== TMA producer: input row pairs (y0-1+2v, y0+2v), v = 0 .. npairs =====================

@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(kSlabwThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();  // programmatic dependent launch: see launch_pdl()
+  grid_dep_wait();    // nothing above reads an activation; everything below may
 
   if (warp == 0) {
     // ===================== TMA producer: per pass and chunk -- two slabs, then the nine weight tiles ==========

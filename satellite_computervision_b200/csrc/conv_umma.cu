@@ -15,22 +15,20 @@ cudaError_t launch_one(const ConvLaunch& L, cudaStream_t stream) {
     if (L.p.ntaps != NTAPS) return cudaErrorInvalidValue;
     if (L.nacc == 4) {
       if constexpr (slab_nacc_ok(BN, 4))
-        conv_slab_kernel<KC, BN, EPI, NTAPS, 4>
-            <<<L.grid, slab_threads(4), L.smem, stream>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+        SCV_LAUNCH_CHECK(launch_pdl(conv_slab_kernel<KC, BN, EPI, NTAPS, 4>, L.grid, slab_threads(4), L.smem, stream, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
       else
         return cudaErrorInvalidValue;
     } else {
-      conv_slab_kernel<KC, BN, EPI, NTAPS, 2>
-          <<<L.grid, slab_threads(2), L.smem, stream>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+      SCV_LAUNCH_CHECK(launch_pdl(conv_slab_kernel<KC, BN, EPI, NTAPS, 2>, L.grid, slab_threads(2), L.smem, stream, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
     }
   } else {
-    conv_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+    SCV_LAUNCH_CHECK(launch_pdl(conv_umma_kernel<KC, BN, EPI>, L.grid, kConvThreads, L.smem, stream, L.tmA, L.tmB, L.p));
   }
   return cudaGetLastError();
 }
 template <int KC, int BN, int EPI>
 cudaError_t launch_ptile(const ConvLaunch& L, cudaStream_t stream) {
-  conv_ptile_kernel<KC, BN, EPI><<<L.grid, kPtileThreads, L.smem, stream>>>(L.tmA, L.tmB, L.p);
+  SCV_LAUNCH_CHECK(launch_pdl(conv_ptile_kernel<KC, BN, EPI>, L.grid, kPtileThreads, L.smem, stream, L.tmA, L.tmB, L.p));
   return cudaGetLastError();
 }
 template <int KC, int BN, int EPI>
@@ -100,18 +98,18 @@ cudaError_t launch_kc8(const ConvLaunch& L, cudaStream_t s) {
   if constexpr (slab_nacc_ok(BN, 4)) {
     if (L.nacc == 4) {
       if (L.EPI == EPI_STORE)
-        conv_slab_kernel<8, BN, EPI_STORE, 9, 4><<<L.grid, slab_threads(4), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+        SCV_LAUNCH_CHECK(launch_pdl(conv_slab_kernel<8, BN, EPI_STORE, 9, 4>, L.grid, slab_threads(4), L.smem, s, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
       else if (L.EPI == EPI_POOL_SKIP)
-        conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 4><<<L.grid, slab_threads(4), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+        SCV_LAUNCH_CHECK(launch_pdl(conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 4>, L.grid, slab_threads(4), L.smem, s, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
       else
         return cudaErrorInvalidValue;
       return cudaGetLastError();
     }
   }
   if (L.EPI == EPI_STORE)
-    conv_slab_kernel<8, BN, EPI_STORE, 9, 2><<<L.grid, slab_threads(2), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+    SCV_LAUNCH_CHECK(launch_pdl(conv_slab_kernel<8, BN, EPI_STORE, 9, 2>, L.grid, slab_threads(2), L.smem, s, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
   else if (L.EPI == EPI_POOL_SKIP)
-    conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 2><<<L.grid, slab_threads(2), L.smem, s>>>(L.tmA, L.tmB, L.tmOut, L.tmPool, L.p);
+    SCV_LAUNCH_CHECK(launch_pdl(conv_slab_kernel<8, BN, EPI_POOL_SKIP, 9, 2>, L.grid, slab_threads(2), L.smem, s, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

@@ -18,6 +18,8 @@
 //                     deep layers (large Cin*Cout, few pixels).
 //   conv_slab_kernel  persistent + weight-stationary, for the high-resolution layers (see below).
 #pragma once
+#include <cstdlib>
+
 #include "ptx.cuh"
 
 namespace scv {
@@ -54,12 +56,44 @@ struct ConvParams {
   int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
   int dbg;              // timing experiments only (env SCV_ROWS_DBG; results are wrong when non-zero)
-  int linear_out;       // row kernel, experiment: bf16 outputs leave the staging tile through ordinary coalesced stores
-                        // instead of TMA stores (no faster: see conv_rows.cuh)
+  int linear_out;       // bf16 outputs leave the staging tile through ordinary coalesced stores instead of TMA stores:
+                        // row kernel = experiment (no faster, conv_rows.cuh); slab-kernel transposed conv = see epilogue_slab
   // watchdog
   int* err;
   unsigned long long watchdog_ns;
 };
+
+// Programmatic dependent launch (experiment, SCV_PDL=1; off by default): the conv kernels can be launched with
+// programmatic stream serialization so that a layer's prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// epilogue constants) runs while the previous layer drains; grid_dep_wait() sits right after the prologue, before the
+// first read of an activation.  Measured on the full scene: 124.5-124.8 ms with it, 123.3-123.5 ms without
+// (tools/r02_exp14.sh) -- with one 200 KB CTA per SM there is nothing for the early CTAs to overlap with.
+inline bool pdl_enabled() {
+  static const int on = [] {
+    const char* s = getenv("SCV_PDL");
+    return (s && *s) ? atoi(s) : 0;
+  }();
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define SCV_LAUNCH_CHECK(expr)          \
+  do {                                  \
+    cudaError_t _le = (expr);           \
+    if (_le != cudaSuccess) return _le; \
+  } while (0)
 
 constexpr int kConvThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int kMaxHeadClasses = 16;
@@ -258,6 +292,40 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const CUtenso
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    if constexpr (EPI == EPI_CONVT) {
+      if (p.linear_out) {
+        // Experiment (SCV_LSU_CONVT=1, off): transposed conv through the LSU instead of the TMA store this epilogue
+        // waits for (ncu: 25 % of the stall samples on the staging-release wait).  Linear staging, read back 8 pixels
+        // x 64 B per warp instruction, 128-bit stores.  Measured: dec0.up 6.2 vs 6.5 ms, dec1.up 4.6 vs 2.9 ms,
+        // dec2.up 2.5 vs 1.7 ms -- the store path is not the limiter; these layers run at ~77 % of the write-heavy
+        // HBM ceiling (tools/microbench/hbm_rw_mix.cu) and only fusing them into their consumer removes the traffic.
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c = (static_cast<uint32_t>(j) + phase) & 3;
+          const uint32_t a0 = c == 0 ? pk[0] : (c == 1 ? pk[4] : (c == 2 ? pk[8] : pk[12]));
+          const uint32_t a1 = c == 0 ? pk[1] : (c == 1 ? pk[5] : (c == 2 ? pk[9] : pk[13]));
+          const uint32_t a2 = c == 0 ? pk[2] : (c == 1 ? pk[6] : (c == 2 ? pk[10] : pk[14]));
+          const uint32_t a3 = c == 0 ? pk[3] : (c == 1 ? pk[7] : (c == 2 ? pk[11] : pk[15]));
+          sts128(out_row + (c << 4), a0, a1, a2, a3);
+        }
+        __syncwarp();
+        const int ch0 = nb0 + blk * 32;
+        const int g = ch0 / p.Cout;  // sub-pixel (a, b) = (g >> 1, g & 1)
+        const int sx = lane >> 2, c16 = (lane & 3) * 16;
+        uint4 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = lds128(smem_u32(stage) + k * 512 + lane * 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // staging row k * 8 + sx = tile pixel (x0 + sx, y0 + 4 q + k)
+          const size_t oy = static_cast<size_t>(n) * (2 * p.H) + 2 * (y0 + q * 4 + k) + (g >> 1);
+          const size_t ox = 2 * (x0 + sx) + (g & 1);
+          uint8_t* gp = reinterpret_cast<uint8_t*>(p.out) + ((oy * (2 * p.W) + ox) * p.out_pitch + p.out_choff + (ch0 - g * p.Cout)) * 2 + c16;
+          *reinterpret_cast<uint4*>(gp) = t[k];
+        }
+        continue;
+      }
+    }
     if (lane == 0) bulk_wait_read<0>();  // this warp's previous store has finished reading the staging tile
     __syncwarp();
 #pragma unroll
@@ -403,6 +471,8 @@ __global__ void __launch_bounds__(kConvThreads)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();  // programmatic dependent launch: see launch_pdl()
+  grid_dep_wait();    // nothing above reads an activation; everything below may
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform loop, elected issue) =====================
@@ -567,6 +637,8 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();  // programmatic dependent launch: see launch_pdl()
+  grid_dep_wait();    // nothing above reads an activation; everything below may
 
   if (warp == 0) {
     // ===================== TMA producer: one uninterrupted stage stream over all tiles of this CTA ==========
@@ -815,6 +887,8 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();  // programmatic dependent launch: see launch_pdl()
+  grid_dep_wait();    // nothing above reads an activation; everything below may
 
   if (warp == 0) {
     // ===================== TMA producer =====================

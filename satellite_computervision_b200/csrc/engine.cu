@@ -766,13 +766,15 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   }
   // weight-streaming halo-slab kernel: Cout = 128 layers whose 3x3 weights exceed shared memory (conv_slabw.cuh);
   // same summation order as the slab / tile kernels, so the choice may depend on the batch size
-  if (env_int("SCV_SLABW", 1) && l.kind == L_CONV3 && l.KC == 64 && l.ntotal == 128 &&
+  const bool slabw_n64 = l.ntotal == 64 && l.cin_pad >= 128 && env_int("SCV_SLABW_N64", 0);  // measured slower (14.4 vs 12.0 ms): off
+  if (env_int("SCV_SLABW", 1) && l.kind == L_CONV3 && l.KC == 64 && (l.ntotal == 128 || slabw_n64) &&
       l.cin_pad >= env_int("SCV_SLABW_MIN_CIN", 64) && (l.epi == EPI_STORE || l.epi == EPI_POOL_SKIP) && w % 8 == 0 && h % 16 == 0 &&
       ((long long)B * (h / 16) * (w / 8) >= 4LL * sm_count() || env_int("SCV_SLABW", 1) == 2)) {
-    int nbr = 6;
-    while (nbr > 2 && slabw_smem_bytes(64, 128, nbr, l.epi) > kSlabSmemBudget) --nbr;
+    const int wn = l.ntotal;
+    int nbr = wn == 64 ? 10 : 6;
+    while (nbr > 2 && slabw_smem_bytes(64, wn, nbr, l.epi) > kSlabSmemBudget) --nbr;
     L->slab = 4;
-    L->BN = 128;
+    L->BN = wn;
     L->nacc = 4;
     p.TW = 8, p.TH = 16, p.TN = 1;
     p.tiles_x = w / 8;
@@ -783,8 +785,8 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     p.nstage = nbr;
     p.n_issuers = std::max(1, std::min(kSlabwIssuers, env_int("SCV_SLABW_ISSUERS", kSlabwIssuers)));
     L->grid = (int)std::min<long long>(sm_count(), p.num_m_tiles);
-    L->smem = slabw_smem_bytes(64, 128, nbr, l.epi);
-    if (l.BN != 128) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, 128));
+    L->smem = slabw_smem_bytes(64, wn, nbr, l.epi);
+    if (l.BN != wn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, wn));
     else L->tmB = l.tmB;
     SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, 10, 18, 1));
     return SCV_OK;
@@ -924,6 +926,7 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
     // the 384 x 384 layers.
     if (Ln.slab == 2 && (l.epi == EPI_STORE || l.epi == EPI_POOL_SKIP) && env_int("SCV_LSU_STORE", 0))
       p.linear_out = 1;
+    if (Ln.slab == 1 && l.epi == EPI_CONVT && env_int("SCV_LSU_CONVT", 0)) p.linear_out = 1;  // slab kernel, transposed conv (experiment: slower at 128-byte pitch)
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
       fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,

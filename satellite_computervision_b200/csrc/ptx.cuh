@@ -30,6 +30,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------ programmatic dependent launch
+// wait: blocks until every grid this one depends on has completed and its memory is visible (a no-op when the
+// launch carried no programmatic-serialization attribute); launch_dependents: the next grid in the stream may be
+// scheduled as soon as every CTA of this one has executed it (or exited).
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

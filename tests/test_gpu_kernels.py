@@ -140,6 +140,8 @@ def test_persistent_tile_kernel_equals_tile_kernel(N, H, W, Cin, Cout, grid, mon
     (1, 48, 96, 256, 128, 3),     # 4 chunks, 36 tiles over 3 CTAs: 6 two-tile passes each, rings wrap
     (3, 16, 24, 128, 128, 2),     # 9 tiles over 2 CTAs: odd tile counts -> a one-tile tail pass
     (1, 32, 16, 64, 128, 1),      # one chunk
+    (2, 32, 48, 128, 64, 3),      # Cout = 64 with two chunks (decoder_1/conv0 at 192x192): N = 64 weight tiles, 10-deep ring
+    (1, 48, 32, 256, 64, 2),
 ])
 def test_weight_streaming_slab_kernel(N, H, W, Cin, Cout, grid, monkeypatch):
     """conv_slabw_kernel (halo slabs + streamed weights shared by two M tiles) against torch and, bit for bit,
