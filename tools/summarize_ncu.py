@@ -50,5 +50,43 @@ def full(src, dst):
             f.write(f'| `{name}` | {r[gi]} | ' + ' | '.join(r[i] for i in idx.values()) + ' |\n')
 
 
+
+
+def layers(src, dst, names=None):
+    """by-name metric capture of one device batch (long CSV: one row per kernel and metric) -> per-layer table +
+    DRAM bytes per chip (profiles/rNN_conv_traffic.json)."""
+    import json
+    lines = [ln for ln in open(src) if ln.startswith('"')]
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        k = int(row['ID'])
+        per.setdefault(k, {'kernel': row['Kernel Name'].split('(')[0].replace('void ', '').replace('scv::', ''), 'grid': row['Grid Size']})
+        per[k][row['Metric Name']] = float(row['Metric Value'].replace(',', ''))
+    short = {'gpu__time_duration.sum': 'us', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active': 'tensor%',
+             'sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed': 'tc%', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed': 'dram%',
+             'lts__throughput.avg.pct_of_peak_sustained_elapsed': 'lts%', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed': 'l1tex%',
+             'sm__throughput.avg.pct_of_peak_sustained_elapsed': 'sm%', 'dram__bytes_read.sum': 'DRAM rd MB', 'dram__bytes_write.sum': 'DRAM wr MB',
+             'launch__registers_per_thread': 'regs'}
+    rows = [v for v in per.values()]
+    conv = [r for r in rows if 'conv_' in r['kernel']]
+    nchips = int(sys.argv[4]) if len(sys.argv) > 4 else 63
+    with open(dst, 'w') as f:
+        f.write(f'# ncu by-name metrics of one device batch ({nchips} chips) ({src}), --clock-control none\n\n')
+        f.write('| # | kernel | grid | ' + ' | '.join(short.values()) + ' |\n|---|---|---|' + '---|' * len(short) + '\n')
+        for i, r in enumerate(rows):
+            vals = []
+            for k, s in short.items():
+                v = r.get(k, 0.0)
+                vals.append(f'{v / 1e3:.1f}' if s == 'us' else (f'{v / 1e6:.1f}' if 'MB' in s else f'{v:.1f}'))
+            f.write(f'| {i} | `{r["kernel"]}` | {r["grid"]} | ' + ' | '.join(vals) + ' |\n')
+        tot_us = sum(r['gpu__time_duration.sum'] for r in conv) / 1e3
+        tot_b = sum(r['dram__bytes_read.sum'] + r['dram__bytes_write.sum'] for r in conv)
+        f.write(f'\n{len(conv)} conv launches: {tot_us:.0f} us, {tot_b / 1e9:.2f} GB of DRAM traffic for {nchips} chips = '
+                f'{tot_b / nchips / 1e6:.1f} MB per chip (algorithmic FLOPs 67.41 GFLOP per chip -> '
+                f'{67.41e9 * nchips / (tot_us * 1e-6) / 1e12:.0f} TFLOP/s under ncu clocks).\n')
+    with open(dst.replace('_all_layers_metrics.md', '_conv_traffic.json'), 'w') as f:
+        json.dump({'dram_bytes_per_chip': tot_b / nchips, 'conv_launches': len(conv), 'chips': nchips, 'source': src}, f)
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'layers': layers}[sys.argv[1]](sys.argv[2], sys.argv[3])
