@@ -451,123 +451,89 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
           mbar_arrive(&acc_empty[slot]);
         } else {
 #pragma unroll
-          for (int b = 0; b < COUT / 32; ++b) {
-            uint32_t raw0[32], raw1[32];
-            const long long tl0 = ROWS_CLOCK();
-            tmem_ld32(taddr + b * 32, raw0);
-            tmem_ld32(taddr + COUT + b * 32, raw1);
-            tmem_ld_wait();
-            const long long tl1 = ROWS_CLOCK();
-            t_ld += tl1 - tl0;
-            if (b == COUT / 32 - 1) {  // everything read: zero both accumulators and hand them back
-              if (!(p.dbg & 2)) {
-#pragma unroll
-                for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
-                tmem_st_wait();
-              }
-              tc_fence_before();
-              mbar_arrive(&acc_empty[slot]);
-            }
-            t_zero += ROWS_CLOCK() - tl1;
-            if (p.dbg & 1) continue;
+          for (int b = 0; b < COUT / 32; ++b) {  // one staging tile / TMA store per 32-channel block
             const long long ts0 = ROWS_CLOCK();
-            // Two ways out of the staging tile.  TMA (default): swizzled rows, one tensor-map store per tile.
-            // LSU (p.linear_out, experiment): LINEAR rows (a lane rotates which 16-byte chunk it writes per step, so the
-            // shared-memory stores stay conflict free), read back 512 contiguous bytes per warp instruction and written
-            // with ordinary coalesced 128-bit stores.  Both cost the same on the 384 x 384 layers (~11.5 B/clk per SM
-            // of output whatever the path, profiles/r02_store_path.md), so the store path is not the limiter.
-            const bool lsu = p.linear_out != 0;
-            if (!lsu && lane == 0) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
+            if (lane == 0) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
             __syncwarp();
             t_st += ROWS_CLOCK() - ts0;
             const uint32_t row0 = smem_u32(stage) + lane * 64;
-            float v[32];
-            uint32_t pk[16], w0[16];
-            auto put = [&](uint32_t rowaddr, const uint32_t (&qv)[16], uint32_t key) {
-              if (lsu) {
+            // 16 channels at a time: two row halves (2 x 16 accumulator columns) + their constants stay in registers;
+            // the 32-column form spilled 116-144 B per thread in the pooling epilogue (ptxas -v) -- local-memory traffic
+            // in the stage that bounds the K-short 384 x 384 layers (profiles/r02_store_path.md, ablation table)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t c = (static_cast<uint32_t>(j) + key) & 3;
-                  const uint32_t a0 = c == 0 ? qv[0] : (c == 1 ? qv[4] : (c == 2 ? qv[8] : qv[12]));
-                  const uint32_t a1 = c == 0 ? qv[1] : (c == 1 ? qv[5] : (c == 2 ? qv[9] : qv[13]));
-                  const uint32_t a2 = c == 0 ? qv[2] : (c == 1 ? qv[6] : (c == 2 ? qv[10] : qv[14]));
-                  const uint32_t a3 = c == 0 ? qv[3] : (c == 1 ? qv[7] : (c == 2 ? qv[11] : qv[15]));
-                  sts128(rowaddr + (c << 4), a0, a1, a2, a3);
+            for (int h = 0; h < 2; ++h) {
+              const int col = b * 32 + h * 16;
+              uint32_t r0[16], r1[16];
+              const long long tl0 = ROWS_CLOCK();
+              tmem_ld16(taddr + col, r0);
+              tmem_ld16(taddr + COUT + col, r1);
+              tmem_ld_wait();
+              const long long tl1 = ROWS_CLOCK();
+              t_ld += tl1 - tl0;
+              if (b == COUT / 32 - 1 && h == 1) {  // everything read: zero both accumulators and hand them back
+                if (!(p.dbg & 2)) {
+#pragma unroll
+                  for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
+                  tmem_st_wait();
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[slot]);
+              }
+              t_zero += ROWS_CLOCK() - tl1;
+              if (p.dbg & 1) continue;
+              float bias[16];
+              lds16(s_bias + col, bias);
+              uint32_t pk0[8], pk1[8];  // packed bf16 pairs of rows y and y+1
+              if constexpr (EPI == EPI_POOL_SKIP) {
+                float sc[16], sh[16];
+                lds16(s_extra + col, sc);
+                lds16(s_extra + COUT + col, sh);
+                uint32_t pm[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  // conv output relu(acc + bias) feeds the pool (bf16-rounded; rounding is monotonic, so max commutes
+                  // with it) and, through the decoder's post-concat BN + ReLU, the skip half of the concat buffer
+                  float a0 = __uint_as_float(r0[2 * j]) + bias[2 * j], a1 = __uint_as_float(r0[2 * j + 1]) + bias[2 * j + 1];
+                  float c0 = __uint_as_float(r1[2 * j]) + bias[2 * j], c1 = __uint_as_float(r1[2 * j + 1]) + bias[2 * j + 1];
+                  if (p.relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f), c0 = fmaxf(c0, 0.f), c1 = fmaxf(c1, 0.f);
+                  const uint32_t m = max_bf16x2(pack_bf16x2(a0, a1), pack_bf16x2(c0, c1));
+                  pm[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                  pk0[j] = pack_bf16x2(fmaxf(fmaf(a0, sc[2 * j], sh[2 * j]), 0.f), fmaxf(fmaf(a1, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+                  pk1[j] = pack_bf16x2(fmaxf(fmaf(c0, sc[2 * j], sh[2 * j]), 0.f), fmaxf(fmaf(c1, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+                }
+                if (!(lane & 1)) {
+                  const uint32_t pp = lane >> 1;  // pooled pixel of this warp
+                  const uint32_t prow = smem_u32(stage) + 2 * 32 * 64 + pp * 64;
+                  const uint32_t pph = (pp >> 1) & 3;
+                  sts128(prow + ((static_cast<uint32_t>(2 * h) ^ pph) << 4), pm[0], pm[1], pm[2], pm[3]);
+                  sts128(prow + ((static_cast<uint32_t>(2 * h + 1) ^ pph) << 4), pm[4], pm[5], pm[6], pm[7]);
                 }
               } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  sts128(rowaddr + ((static_cast<uint32_t>(j) ^ key) << 4), qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
-              }
-            };
-            // ---- row y
-            rows_bias_relu(raw0, s_bias + b * 32, p.relu, v);
-            if constexpr (EPI == EPI_POOL_SKIP) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) w0[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-              rows_skip_affine(s_extra + b * 32, s_extra + COUT + b * 32, v);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            put(row0, pk, phase);  // (lane >> 1) & 3: SWIZZLE_64B phase of the row == a conflict-free rotation
-            // ---- row y+1
-            rows_bias_relu(raw1, s_bias + b * 32, p.relu, v);
-            if constexpr (EPI == EPI_POOL_SKIP) {
-              // 2x2 max-pool on the bf16-rounded values (rounding is monotonic, so max commutes with it)
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const uint32_t m = max_bf16x2(w0[j], pack_bf16x2(v[2 * j], v[2 * j + 1]));
-                w0[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, 1));
-              }
-              if (!(lane & 1)) {
-                const uint32_t pp = lane >> 1;  // pooled pixel of this warp
-                put(smem_u32(stage) + 2 * 32 * 64 + pp * 64, w0, (pp >> 1) & 3);
-              }
-              rows_skip_affine(s_extra + b * 32, s_extra + COUT + b * 32, v);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            put(row0 + 32 * 64, pk, phase);
-            const long long tf0 = ROWS_CLOCK();
-            if (lsu) {
-              __syncwarp();
-              if (!(p.dbg & 16)) {
-                const uint32_t sub = lane >> 2, c16 = (lane & 3) * 16;  // pixel within a group of 8, 16-byte chunk of its 64 B
-                if (p.out != nullptr) {
-#pragma unroll
-                  for (int r = 0; r < 2; ++r) {
-                    uint8_t* g = reinterpret_cast<uint8_t*>(p.out) +
-                                 (((static_cast<size_t>(sg.n) * p.H + y + r) * p.W + xw + sub) * p.out_pitch + p.out_choff + b * 32) * 2 + c16;
-                    const size_t px8 = static_cast<size_t>(8) * p.out_pitch * 2;
-                    uint4 t[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) t[k] = lds128(smem_u32(stage) + r * 2048 + k * 512 + lane * 16);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(g + k * px8) = t[k];
+                for (int j = 0; j < 8; ++j) {
+                  pk0[j] = pack_bf16x2(__uint_as_float(r0[2 * j]) + bias[2 * j], __uint_as_float(r0[2 * j + 1]) + bias[2 * j + 1]);
+                  pk1[j] = pack_bf16x2(__uint_as_float(r1[2 * j]) + bias[2 * j], __uint_as_float(r1[2 * j + 1]) + bias[2 * j + 1]);
+                  if (p.relu) {  // relu(round(x)) == round(relu(x)): one packed max per pair instead of two fp32 ones
+                    pk0[j] = max_bf16x2(pk0[j], 0u);
+                    pk1[j] = max_bf16x2(pk1[j], 0u);
                   }
                 }
-                if constexpr (EPI == EPI_POOL_SKIP) {
-                  uint8_t* g = reinterpret_cast<uint8_t*>(p.pool_out) +
-                               (((static_cast<size_t>(sg.n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (xw >> 1) + sub) * p.pool_pitch + b * 32) * 2 + c16;
-                  const size_t px8 = static_cast<size_t>(8) * p.pool_pitch * 2;
-                  uint4 t[2];
-#pragma unroll
-                  for (int k = 0; k < 2; ++k) t[k] = lds128(smem_u32(stage) + 4096 + k * 512 + lane * 16);
-#pragma unroll
-                  for (int k = 0; k < 2; ++k) *reinterpret_cast<uint4*>(g + k * px8) = t[k];
-                }
               }
-              // (the __syncwarp at the top of the next block orders these reads before the next staging writes)
-            } else {
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0 && !(p.dbg & 16)) {
-                if (p.out != nullptr) tma_store_4d(&tmOut, stage, p.out_choff + b * 32, xw, y, sg.n);
-                if constexpr (EPI == EPI_POOL_SKIP) tma_store_4d(&tmPool, stage + 2 * 32 * 64, b * 32, xw >> 1, y >> 1, sg.n);
-                bulk_commit();
-              }
+              sts128(row0 + ((static_cast<uint32_t>(2 * h) ^ phase) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
+              sts128(row0 + ((static_cast<uint32_t>(2 * h + 1) ^ phase) << 4), pk0[4], pk0[5], pk0[6], pk0[7]);
+              sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(2 * h) ^ phase) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
+              sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(2 * h + 1) ^ phase) << 4), pk1[4], pk1[5], pk1[6], pk1[7]);
             }
+            if (p.dbg & 1) continue;
+            const long long tf0 = ROWS_CLOCK();
+            fence_proxy_async();
+            __syncwarp();
             t_fence += ROWS_CLOCK() - tf0;
+            if (lane == 0 && !(p.dbg & 16)) {
+              if (p.out != nullptr) tma_store_4d(&tmOut, stage, p.out_choff + b * 32, xw, y, sg.n);
+              if constexpr (EPI == EPI_POOL_SKIP) tma_store_4d(&tmPool, stage + 2 * 32 * 64, b * 32, xw >> 1, y >> 1, sg.n);
+              bulk_commit();
+            }
           }
         }
       }

@@ -56,8 +56,8 @@ struct ConvParams {
   int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
   int dbg;              // timing experiments only (env SCV_ROWS_DBG; results are wrong when non-zero)
-  int linear_out;       // bf16 outputs leave the staging tile through ordinary coalesced stores instead of TMA stores:
-                        // row kernel = experiment (no faster, conv_rows.cuh); slab-kernel transposed conv = see epilogue_slab
+  int linear_out;       // experiment: the slab kernel's transposed-conv outputs leave the staging tile through ordinary
+                        // coalesced stores instead of TMA stores (see epilogue_slab; no faster)
   // watchdog
   int* err;
   unsigned long long watchdog_ns;

@@ -921,11 +921,6 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
         p.pool_pitch = a.bufs[l.pool_buf].channels;
       }
     }
-    // experiment switch (off): row-kernel outputs through ordinary stores instead of TMA stores.  Measured equal for
-    // EPI_STORE and slower for the pooling epilogue (profiles/r02_store_path.md): the store PATH is not what bounds
-    // the 384 x 384 layers.
-    if (Ln.slab == 2 && (l.epi == EPI_STORE || l.epi == EPI_POOL_SKIP) && env_int("SCV_LSU_STORE", 0))
-      p.linear_out = 1;
     if (Ln.slab == 1 && l.epi == EPI_CONVT && env_int("SCV_LSU_CONVT", 0)) p.linear_out = 1;  // slab kernel, transposed conv (experiment: slower at 128-byte pitch)
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
