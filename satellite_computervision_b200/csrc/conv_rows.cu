@@ -6,7 +6,7 @@ namespace scv {
 namespace {
 template <int KC, int COUT, int EPI>
 cudaError_t rows_one(const ConvLaunch& L, cudaStream_t s) {
-  SCV_LAUNCH_CHECK(launch_pdl(conv_rows_kernel<KC, COUT, EPI>, L.grid, kRowsThreads, L.smem, s, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
+  SCV_LAUNCH_CHECK(launch_pdl(conv_rows_kernel<KC, COUT, EPI>, L.grid, rows_threads(COUT, EPI), L.smem, s, L.tmA, L.tmB, L.tmOut, L.tmPool, L.p));
   return cudaGetLastError();
 }
 template <int KC, int COUT>

@@ -41,10 +41,21 @@ namespace scv {
 #ifndef SCV_ROWS_ISSUERS
 #define SCV_ROWS_ISSUERS 3
 #endif
-constexpr int kRowsEpiGroups = SCV_ROWS_EPI_GROUPS;           // epilogue warpgroups (one output row pair each)
+constexpr int kRowsEpiGroups = SCV_ROWS_EPI_GROUPS;           // epilogue warpgroups (one output row pair each) at Cout 64
+#ifndef SCV_ROWS_EPI_GROUPS32
+#define SCV_ROWS_EPI_GROUPS32 4
+#endif
+// Cout 32 has 8 accumulator pairs and, with the 16-channel epilogue (<= 80 registers), room for a fifth epilogue group
+// (768 threads).  Measured with 5: enc0.c2 8.02 vs 7.89 ms, dec0.c1 8.80 vs 8.67 ms -- no gain, because those two layers
+// already move 5.0 / 6.0 TB/s through HBM (ncu: 1.34 GB in 268 us, 1.77 GB in 296 us per 63 chips), i.e. they sit at the
+// roof of a write-heavy / read-heavy stream.  Left at 4.
+// (the fused-head epilogue would spill at 80 registers and stays at 4 groups in any case; EPI_HEAD == 3)
+__host__ __device__ constexpr int rows_epi_groups(int cout, int epi) {
+  return (cout == 32 && epi != 3) ? SCV_ROWS_EPI_GROUPS32 : kRowsEpiGroups;
+}
 constexpr int kRowsIssuers = SCV_ROWS_ISSUERS;                // MMA issuer warps taking turns (max)
 constexpr int kRowsFirstEpiWarp = 1 + kRowsIssuers;
-constexpr int kRowsThreads = 32 * kRowsFirstEpiWarp + 128 * kRowsEpiGroups;
+__host__ __device__ constexpr int rows_threads(int cout, int epi) { return 32 * kRowsFirstEpiWarp + 128 * rows_epi_groups(cout, epi); }
 constexpr int kRowsPx = 128;                                  // strip width == UMMA M
 constexpr int kRowsSlabPx = kRowsPx + 2;                      // input row with its two halo pixels
 
@@ -56,7 +67,7 @@ __host__ __device__ constexpr int rows_stage_warp_bytes(int epi) {
 }
 __host__ __device__ inline size_t rows_smem_bytes(int KC, int COUT, int cin, int nslab, int epi, int ncls) {
   size_t s = 1024 + static_cast<size_t>(9) * cin * COUT * 2 + static_cast<size_t>(nslab) * rows_slab_stride(KC) +
-             static_cast<size_t>(4 * kRowsEpiGroups) * rows_stage_warp_bytes(epi);
+             static_cast<size_t>(4 * rows_epi_groups(COUT, epi)) * rows_stage_warp_bytes(epi);
   s += (1 + 2 * nslab + 2 * (256 / COUT) + kRowsIssuers) * 8 + 16;
   s += COUT * 4;
   if (epi == EPI_POOL_SKIP) s += 2 * COUT * 4;
@@ -172,7 +183,7 @@ __device__ __forceinline__ void rows_issue_row(uint32_t da0, uint32_t db0, uint3
 }
 
 template <int KC, int COUT, int EPI>
-__global__ void __launch_bounds__(kRowsThreads, 1)
+__global__ void __launch_bounds__(rows_threads(COUT, EPI), 1)
     conv_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPool,
                      const ConvParams p) {
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1)
   constexpr int SLAB_STRIDE = rows_slab_stride(KC);
   constexpr int R = 512 / COUT;              // row accumulators in TMEM
   constexpr int RP = R / 2;                  // ... handed over in pairs
-  constexpr int NG = kRowsEpiGroups;
+  constexpr int NG = rows_epi_groups(COUT, EPI);
   constexpr int NI = kRowsIssuers;
   constexpr int STAGE_W = rows_stage_warp_bytes(EPI);
   static_assert(COUT == 32 || COUT == 64, "row kernel: Cout 32 or 64");

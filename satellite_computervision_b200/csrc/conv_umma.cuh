@@ -371,18 +371,21 @@ __device__ __forceinline__ void epilogue_head(const ConvParams& p, uint32_t tadd
   float acc = s_extra[BN];  // head bias
 #pragma unroll 1
   for (int col = 0; col < BN; col += 32) {
-    uint32_t raw[32];
-    tmem_ld32(taddr + col, raw);
-    float v[32], w[32];
-    lds32(s_bias + col, v);
-    lds32(s_extra + col, w);
-    tmem_ld_wait();
-    float part[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent FMA chains
+    float part[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent FMA chains over the 32 columns of this step
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float t = v[j] + __uint_as_float(raw[j]);
-      if (p.relu) t = fmaxf(t, 0.f);
-      part[j & 3] = fmaf(t, w[j], part[j & 3]);
+    for (int h = 0; h < 2; ++h) {  // 16 accumulator columns at a time (register pressure); the order of the sums is that
+      uint32_t raw[16];            // of one 32-column pass
+      tmem_ld16(taddr + col + 16 * h, raw);
+      float v[16], w[16];
+      lds16(s_bias + col + 16 * h, v);
+      lds16(s_extra + col + 16 * h, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float t = v[j] + __uint_as_float(raw[j]);
+        if (p.relu) t = fmaxf(t, 0.f);
+        part[j & 3] = fmaf(t, w[j], part[j & 3]);
+      }
     }
     acc += (part[0] + part[1]) + (part[2] + part[3]);
   }

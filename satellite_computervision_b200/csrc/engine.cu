@@ -745,7 +745,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     p.Cin = cin;
     p.dbg = env_int("SCV_ROWS_DBG", 0);
     L->BN = l.cout;
-    L->nacc = kRowsEpiGroups;
+    L->nacc = rows_epi_groups(l.cout, l.epi);
     p.TW = kRowsPx, p.TH = 1, p.TN = 1;
     p.tiles_x = w / kRowsPx;
     p.tiles_y = h;

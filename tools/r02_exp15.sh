@@ -2,8 +2,8 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -4
 B="python bench.py --steps 3 --warmup 2 --no-cpu-baseline --profile-layers"
-$B > gpurun_out/r02_r_epi16.json 2> gpurun_out/r02_r_epi16.err
-python - gpurun_out/r02_r_epi16.json <<'P'
+$B > gpurun_out/r02_s_ng5.json 2> gpurun_out/r02_s_ng5.err
+python - gpurun_out/r02_s_ng5.json <<'P'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
