@@ -128,6 +128,8 @@ cudaError_t attr_kc8() {
 }
 
 cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.slab < 0) return cudaSuccess;  // folded into the previous (fused) launch
+  if (L.slab == 5) return conv_fused_launch(L, stream);
   if (L.slab == 2) return conv_rows_launch(L, stream);
   if (L.slab == 4) return conv_slabw_launch(L, stream);
   if (L.KC == 8) {
@@ -161,6 +163,7 @@ cudaError_t conv_init_attributes() {
   if ((e = attr_bn<64>()) != cudaSuccess) return e;
   if ((e = conv_rows_init_attributes()) != cudaSuccess) return e;
   if ((e = conv_slabw_init_attributes()) != cudaSuccess) return e;
+  if ((e = conv_fused_init_attributes()) != cudaSuccess) return e;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }

@@ -39,6 +39,7 @@ struct ConvParams {
   __nv_bfloat16* out;
   int out_pitch, out_choff;
   const float* bias;  // [Ntotal]
+  const float* bias2; // fused two-conv kernel (conv_fused.cuh): bias of the second conv
   int Cout;           // EPI_CONVT: channels per (a,b) sub-pixel, Ntotal == 4*Cout
   // EPI_POOL_SKIP
   __nv_bfloat16* pool_out;
@@ -1055,10 +1056,11 @@ __host__ __device__ inline size_t slab_smem_bytes(int KC, int BN, int ntaps, int
 // Host side -------------------------------------------------------------------
 struct ConvLaunch {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmB2;           // fused two-conv kernel: weights of the second conv
   CUtensorMap tmOut, tmPool;  // slab kernel only: TMA-store maps of the bf16 outputs
   ConvParams p;
   int KC, BN, EPI;
-  int slab;  // 4: conv_slabw_kernel (conv_slabw.cuh), 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
+  int slab;  // 5: conv_fused2_kernel (conv_fused.cuh; the next layer's launch is then -1 = folded into this one), 4: conv_slabw_kernel (conv_slabw.cuh), 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
   int nacc;  // slab kernel: accumulators / epilogue warpgroups (2 or 4)
   int grid;
   size_t smem;
@@ -1068,6 +1070,10 @@ struct ConvLaunch {
 cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream);
 // Sets the max-dynamic-smem attribute of every instantiation (once per device).
 cudaError_t conv_init_attributes();
+// conv_fused.cu
+cudaError_t conv_fused_launch(const ConvLaunch& L, cudaStream_t stream);
+cudaError_t conv_fused_init_attributes();
+int conv_fused_max_clusters(size_t smem);
 // conv_rows.cu
 cudaError_t conv_rows_launch(const ConvLaunch& L, cudaStream_t stream);
 cudaError_t conv_rows_init_attributes();

@@ -18,6 +18,7 @@
 
 #include "../../include/scv.h"
 #include "conv_rows.cuh"
+#include "conv_fused.cuh"
 #include "conv_slabw.cuh"
 #include "conv_umma.cuh"
 #include "tile_kernels.cuh"
@@ -930,6 +931,33 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
               Ln.slab == 3 ? 2 : (Ln.slab ? Ln.nacc : 1), Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
+  // Fuse decoder_0/conv0 -> decoder_0/conv1 + head into one cluster launch (conv_fused.cuh) when both run in the row
+  // kernel on 384-pixel rows: the 32-channel intermediate then never goes to HBM.  Bit-identical to the two launches.
+  for (size_t i = 0; i + 1 < a.layers.size() && env_int("SCV_FUSE", 1); ++i) {
+    const LayerDef &l1 = a.layers[i], &l2 = a.layers[i + 1];
+    ConvLaunch &A = pl->launches[i], &Bn = pl->launches[i + 1];
+    if (A.slab != 2 || Bn.slab != 2 || l1.epi != EPI_STORE || l2.epi != EPI_HEAD || l1.cout != 32 || l2.cout != 32 ||
+        l1.cin_pad != 64 || l1.KC != 64 || l2.cin_pad != 32 || l2.in_buf != l1.out_buf || l1.level != 0 || l2.level != 0 ||
+        W != kF2Cluster * kRowsPx || (H & 1))
+      continue;
+    const size_t smem = fused_smem_bytes(64, a.cfg.nclasses);
+    if (smem > 227 * 1024) continue;
+    const int ncl = conv_fused_max_clusters(smem);
+    if (ncl < 8) continue;  // cluster launch not available / too few co-resident clusters: keep the two launches
+    A.slab = 5;
+    A.tmB2 = Bn.tmB;
+    A.p.bias2 = l2.d_bias;
+    A.p.head_w = Bn.p.head_w;
+    A.p.head_b = Bn.p.head_b;
+    A.p.ncls = Bn.p.ncls;
+    A.p.logits = Bn.p.logits;
+    A.smem = smem;
+    A.grid = kF2Cluster * (int)std::min<long long>(ncl, (long long)B * (H / 2));
+    Bn.slab = -1;
+    if (env_int("SCV_PLAN_DEBUG", 0))
+      fprintf(stderr, "[scv plan B=%d] %s + %s fused: %d clusters of %d CTAs, smem=%zu\n", B, l1.name.c_str(), l2.name.c_str(),
+              A.grid / kF2Cluster, kF2Cluster, smem);
+  }
   *out = pl.get();
   e->plans.push_back(std::move(pl));
   return SCV_OK;
@@ -963,7 +991,8 @@ static int run_layers(scv_engine* e, Plan* pl, int tile_off, int side, cudaStrea
     ConvLaunch L = pl->launches[i];
     const LayerDef& l = a.layers[i];
     if (l.in_buf == a.x0_buf) L.p.n_in_off = tile_off;
-    if (l.epi == EPI_HEAD) L.p.logits = e->d_logits_all + (size_t)tile_off * side * side * a.cfg.nclasses;
+    if (l.epi == EPI_HEAD || L.slab == 5) L.p.logits = e->d_logits_all + (size_t)tile_off * side * side * a.cfg.nclasses;
+    if (L.slab < 0) continue;  // folded into the previous (fused) launch
     cudaError_t err = conv_launch(L, s);
     if (err != cudaSuccess)
       return fail(SCV_ERR_CUDA, "launch of layer %s failed: %s", l.name.c_str(), cudaGetErrorString(err));
