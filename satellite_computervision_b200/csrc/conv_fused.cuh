@@ -29,25 +29,28 @@ namespace scv {
 
 constexpr int kF2Issuers1 = 2, kF2Issuers2 = 2;                   // issuer warps per conv (taking turns: a single issuer
                                                                   // spends > 1000 cycles per row on waits and commits)
-constexpr int kF2Groups1 = 2, kF2Groups2 = 2;                     // epilogue warpgroups per conv
+// epilogue warpgroups per conv: the decoder tail (fused head) splits them 2 + 2; the encoder pair, whose second
+// epilogue pools, applies the skip affine and stores two tensors, 1 + 3
+__host__ __device__ constexpr int f2_groups1(int epi2) { return epi2 == EPI_POOL_SKIP ? 1 : 2; }
+__host__ __device__ constexpr int f2_groups2(int epi2) { return epi2 == EPI_POOL_SKIP ? 3 : 2; }
 constexpr int kF2Issuer2Warp = 1 + kF2Issuers1;                   // warp 0: TMA, 1..2: conv-1 issuers, 3..4: conv-2 issuers
 constexpr int kF2FirstEpi1 = 8;                                   // warps 5..7 idle (TMEM lane quadrant == warp & 3)
-constexpr int kF2FirstEpi2 = kF2FirstEpi1 + 4 * kF2Groups1;       // 16
-constexpr int kF2Threads = 32 * (kF2FirstEpi2 + 4 * kF2Groups2);  // 768
+constexpr int kF2Threads = 32 * (kF2FirstEpi1 + 4 * 4);           // 768: four epilogue warpgroups in total
 constexpr int kF2R = 8;                                           // row accumulators per conv: 8 x 32 columns = 256
 constexpr int kF2RP = kF2R / 2;
 constexpr int kF2InSlabs = 3;                                     // conv-1 input slabs (two rows of 130 px x 64 ch)
 constexpr int kF2Ring = 4;                                        // conv-1 -> conv-2 slabs (two rows of 130 px x 32 ch)
 constexpr int kF2Cluster = 3;                                     // strips per image row
-static_assert(kF2FirstEpi1 % 4 == 0 && kF2FirstEpi2 % 4 == 0, "epilogue warps must start on a TMEM quadrant boundary");
-static_assert(kF2RP >= kF2Groups1 && kF2RP >= kF2Groups2 && kF2RP >= kF2Issuers1 && kF2RP >= kF2Issuers2, "accumulator reuse distance");
+static_assert(kF2FirstEpi1 % 4 == 0, "epilogue warps must start on a TMEM quadrant boundary");
+static_assert(kF2RP >= 3 && kF2RP >= kF2Issuers1 && kF2RP >= kF2Issuers2, "accumulator reuse distance (<= 3 groups per conv)");
 static_assert(kF2Issuer2Warp + kF2Issuers2 <= kF2FirstEpi1 && kF2Ring >= kF2Issuers2, "warp layout / ring depth");
 
-__host__ __device__ inline size_t fused_smem_bytes(int KC1, int ncls) {
+__host__ __device__ inline size_t fused_smem_bytes(int KC1, int epi2, int ncls) {
   size_t s = 1024 + static_cast<size_t>(9) * 32 * KC1 * 2 + static_cast<size_t>(9) * 32 * 64 +
-             static_cast<size_t>(kF2InSlabs) * rows_slab_stride(KC1) + static_cast<size_t>(kF2Ring) * rows_slab_stride(32);
+             static_cast<size_t>(kF2InSlabs) * rows_slab_stride(KC1) + static_cast<size_t>(kF2Ring) * rows_slab_stride(32) +
+             static_cast<size_t>(4 * f2_groups2(epi2)) * rows_stage_warp_bytes(epi2);
   s += (1 + 2 * kF2InSlabs + 4 * kF2RP + kF2Issuers1 + kF2Issuers2 + 2 * kF2Ring) * 8 + 16;
-  s += (32 + 32 + 32 * ncls + ncls) * 4;
+  s += (32 + 32 + (epi2 == EPI_HEAD ? 32 * ncls + ncls : 64)) * 4;
   return s + 64;
 }
 
@@ -128,12 +131,19 @@ __device__ __forceinline__ RowsPiece rows_piece_r(uint32_t base, int j, int npai
   return r;
 }
 
-// KC1: channel chunk of conv 1 (== its padded Cin: one chunk); conv 2 is 32 -> 32 with the fused head.
-template <int KC1>
+// KC1: channel chunk of conv 1 (== its padded Cin: one chunk; 16 = the 8-channel first layer read through 16-channel
+// TMA boxes).  Conv 2 is 32 -> 32; EPI2 = EPI_HEAD (decoder tail: fused 1x1 head -> logits) or EPI_POOL_SKIP (encoder
+// pair: 2x2 max-pool + skip affine, two TMA-stored outputs).
+template <int KC1, int EPI2>
 __global__ void __launch_bounds__(kF2Threads, 1)
     conv_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
-                       const __grid_constant__ CUtensorMap tmB2, const ConvParams p) {
+                       const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
+                       const __grid_constant__ CUtensorMap tmPool, const ConvParams p) {
   constexpr int COUT = 32;
+  constexpr int NG1 = f2_groups1(EPI2), NG2 = f2_groups2(EPI2);
+  constexpr int kF2FirstEpi2 = kF2FirstEpi1 + 4 * NG1;
+  constexpr int STAGE_W = rows_stage_warp_bytes(EPI2);
+  static_assert(EPI2 == EPI_HEAD || EPI2 == EPI_POOL_SKIP, "second epilogue: fused head or pool + skip");
   constexpr int ROWB1 = KC1 * 2, WT1 = COUT * ROWB1;        // conv-1 weight tile per (kx, ky)
   constexpr int ROWB2 = 64, WT2 = COUT * ROWB2;             // conv-2: 32 input channels
   constexpr int ROW1 = kRowsSlabPx * ROWB1, SLAB1 = 2 * ROW1, STRIDE1 = rows_slab_stride(KC1);
@@ -147,7 +157,8 @@ __global__ void __launch_bounds__(kF2Threads, 1)
   uint8_t* slabs = ring + static_cast<size_t>(NR) * STRIDE2;
   uint8_t* w1 = slabs + static_cast<size_t>(NS1) * STRIDE1;  // [kx][ky = 2,1,0][32 rows][KC1]
   uint8_t* w2 = w1 + 9 * WT1;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w2 + 9 * WT2);
+  uint8_t* staging = w2 + 9 * WT2;  // epilogue B's TMA-store staging tiles (EPI_POOL_SKIP)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * NG2 * STAGE_W);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* in_empty = in_full + NS1;
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(kF2Threads, 1)
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
   float* s_bias1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
   float* s_bias2 = s_bias1 + COUT;
-  float* s_head = s_bias2 + COUT;  // [32][ncls] + [ncls] (layout of load_epilogue_consts<.., EPI_HEAD>)
+  float* s_head = s_bias2 + COUT;  // EPI_HEAD: [32][ncls] + [ncls]; EPI_POOL_SKIP: skip scale [32] + shift [32]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -177,6 +188,10 @@ __global__ void __launch_bounds__(kF2Threads, 1)
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB1);
     tma_prefetch_desc(&tmB2);
+    if constexpr (EPI2 == EPI_POOL_SKIP) {
+      tma_prefetch_desc(&tmOut);
+      tma_prefetch_desc(&tmPool);
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -210,8 +225,15 @@ __global__ void __launch_bounds__(kF2Threads, 1)
       s_bias1[i] = p.bias[i];
       s_bias2[i] = p.bias2[i];
     }
-    for (int i = t; i < COUT * p.ncls; i += nt) s_head[i] = p.head_w[i];
-    for (int i = t; i < p.ncls; i += nt) s_head[COUT * p.ncls + i] = p.head_b[i];
+    if constexpr (EPI2 == EPI_HEAD) {
+      for (int i = t; i < COUT * p.ncls; i += nt) s_head[i] = p.head_w[i];
+      for (int i = t; i < p.ncls; i += nt) s_head[COUT * p.ncls + i] = p.head_b[i];
+    } else {
+      for (int i = t; i < COUT; i += nt) {
+        s_head[i] = p.skip_s[i];
+        s_head[COUT + i] = p.skip_t[i];
+      }
+    }
   }
   tc_fence_before();
   cluster_sync_all();  // every CTA's barriers exist before any remote arrive (also a CTA-wide barrier)
@@ -382,12 +404,20 @@ __global__ void __launch_bounds__(kF2Threads, 1)
     long long pc = p0;
     RowSeg sg;
     bool run = true;
+    long long ta_acc = 0, ta_free = 0, ta_ld = 0, ta_math = 0, ta_fence = 0, ta_begin = ROWS_CLOCK();
+    uint32_t ta_n = 0;
     while (run && rows_next_seg(pc, p1, 1, H2, sg)) {
       for (int u = 0; u <= sg.npairs; ++u, ++op1) {
-        if (op1 % kF2Groups1 != static_cast<uint32_t>(g)) continue;
+        if (op1 % NG1 != static_cast<uint32_t>(g)) continue;
         const uint32_t slot = op1 % RP, rs = op1 % NR, use = op1 / NR;
+        const long long c0 = ROWS_CLOCK();
         bool ok = mbar_wait(&acc1_full[slot], (op1 / RP) & 1, abort_flag, p.watchdog_ns);
+        const long long c1 = ROWS_CLOCK();
         ok = ok && mbar_wait(&slot_free[rs], (use & 1) ^ 1, abort_flag, p.watchdog_ns);
+        const long long c2 = ROWS_CLOCK();
+        ta_acc += c1 - c0;
+        ta_free += c2 - c1;
+        ++ta_n;
         if (!__all_sync(0xffffffffu, ok)) {
           run = false;
           break;
@@ -402,6 +432,7 @@ __global__ void __launch_bounds__(kF2Threads, 1)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r0[16], r1[16];
+          const long long c3 = ROWS_CLOCK();
           tmem_ld16(taddr + h * 16, r0);
           tmem_ld16(taddr + COUT + h * 16, r1);
           tmem_ld_wait();
@@ -412,6 +443,7 @@ __global__ void __launch_bounds__(kF2Threads, 1)
             tc_fence_before();
             mbar_arrive(&acc1_empty[slot]);
           }
+          ta_ld += ROWS_CLOCK() - c3;
           float bias[16];
           lds16(s_bias1 + h * 16, bias);
           uint32_t pk0[8], pk1[8];
@@ -462,6 +494,7 @@ __global__ void __launch_bounds__(kF2Threads, 1)
             }
           }
         }
+        const long long c4 = ROWS_CLOCK();
         fence_proxy_async_all();  // generic-proxy stores (local and remote) -> visible to the UMMAs that read the slab
         mbar_arrive(&ring_full[rs]);
         if (edge_l) {
@@ -472,42 +505,119 @@ __global__ void __launch_bounds__(kF2Threads, 1)
           if (xs + 1 < kF2Cluster) mbar_arrive_remote(mapa_shared(smem_u32(&ring_full[rs]), xs + 1));
           else mbar_arrive(&ring_full[rs]);
         }
+        ta_fence += ROWS_CLOCK() - c4;
+        ta_math += c4 - c2;
       }
     }
+#ifdef SCV_ROWS_PROF
+    if ((p.dbg & 32) && blockIdx.x < 3 && lane == 0 && q == 0)
+      printf("[fused prof] cta %d epilogue A group %d: total %lld cyc over %u pairs: wait acc1_full %lld, wait slot_free %lld, tmem ld+zero %lld, math+stores (incl. ld) %lld, fence+arrive %lld\n",
+             blockIdx.x, g, ROWS_CLOCK() - ta_begin, ta_n, ta_acc, ta_free, ta_ld, ta_math, ta_fence);
+#endif
   } else {
-    // ===================== epilogue B: conv-2 accumulators -> bias + ReLU + 1x1 head -> logits ===================
+    // ===================== epilogue B: conv-2 accumulators -> fused head (logits) | pool + skip (TMA stores) ======
     const int ew = warp - kF2FirstEpi2;
     const int g = ew >> 2;
     const int q = warp & 3;
     const uint32_t tq = tmem_base + ACC2 + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* stage = staging + static_cast<size_t>(ew) * STAGE_W;
+    const uint32_t phase = (lane >> 1) & 3;  // SWIZZLE_64B phase of staging rows `lane` and `32 + lane`
     uint32_t opc = 0;
     long long pc = p0;
     RowSeg sg;
     bool run = true;
+    long long tb_wait = 0, tb_begin = ROWS_CLOCK();
+    uint32_t tb_n = 0;
     while (run && rows_next_seg(pc, p1, 1, H2, sg)) {
       for (int u = 0; u < sg.npairs; ++u) {
         const uint32_t op = opc + u;
-        if (op % kF2Groups2 != static_cast<uint32_t>(g)) continue;
+        if (op % NG2 != static_cast<uint32_t>(g)) continue;
         const uint32_t slot = op % RP;
+        const long long c0 = ROWS_CLOCK();
         const bool ready = mbar_wait(&acc2_full[slot], (op / RP) & 1, abort_flag, p.watchdog_ns);
+        tb_wait += ROWS_CLOCK() - c0;
+        ++tb_n;
         if (!__all_sync(0xffffffffu, ready)) {
           run = false;
           break;
         }
         tc_fence_after();
         const uint32_t taddr = tq + slot * (2 * COUT);
-        const int x = static_cast<int>(xs) * kRowsPx + q * 32 + lane;
+        const int xw = static_cast<int>(xs) * kRowsPx + q * 32;  // first pixel of this warp
         const int y = sg.y0 + 2 * u;
-        epilogue_head<COUT>(p, taddr, 0, 0, x, y, sg.n, true, 0, s_bias2, s_head);
-        epilogue_head<COUT>(p, taddr + COUT, 0, 0, x, y + 1, sg.n, true, 0, s_bias2, s_head);
+        if constexpr (EPI2 == EPI_HEAD) {
+          epilogue_head<COUT>(p, taddr, 0, 0, xw + lane, y, sg.n, true, 0, s_bias2, s_head);
+          epilogue_head<COUT>(p, taddr + COUT, 0, 0, xw + lane, y + 1, sg.n, true, 0, s_bias2, s_head);
 #pragma unroll
-        for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&acc2_empty[slot]);
+          for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&acc2_empty[slot]);
+        } else {
+          // the row kernel's pooling epilogue (conv_rows.cuh), 16 channels at a time
+          if (lane == 0) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
+          __syncwarp();
+          const uint32_t row0 = smem_u32(stage) + lane * 64;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int col = h * 16;
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr + col, r0);
+            tmem_ld16(taddr + COUT + col, r1);
+            tmem_ld_wait();
+            if (h == 1) {
+#pragma unroll
+              for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(&acc2_empty[slot]);
+            }
+            float bias[16], sc[16], sh[16];
+            lds16(s_bias2 + col, bias);
+            lds16(s_head + col, sc);
+            lds16(s_head + COUT + col, sh);
+            uint32_t pk0[8], pk1[8], pm[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a0 = __uint_as_float(r0[2 * j]) + bias[2 * j], a1 = __uint_as_float(r0[2 * j + 1]) + bias[2 * j + 1];
+              float c0 = __uint_as_float(r1[2 * j]) + bias[2 * j], c1 = __uint_as_float(r1[2 * j + 1]) + bias[2 * j + 1];
+              if (p.relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f), c0 = fmaxf(c0, 0.f), c1 = fmaxf(c1, 0.f);
+              const uint32_t m = max_bf16x2(pack_bf16x2(a0, a1), pack_bf16x2(c0, c1));
+              pm[j] = max_bf16x2(m, __shfl_xor_sync(0xffffffffu, m, 1));
+              pk0[j] = pack_bf16x2(fmaxf(fmaf(a0, sc[2 * j], sh[2 * j]), 0.f), fmaxf(fmaf(a1, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+              pk1[j] = pack_bf16x2(fmaxf(fmaf(c0, sc[2 * j], sh[2 * j]), 0.f), fmaxf(fmaf(c1, sc[2 * j + 1], sh[2 * j + 1]), 0.f));
+            }
+            if (!(lane & 1)) {
+              const uint32_t pp = lane >> 1;  // pooled pixel of this warp
+              const uint32_t prow = smem_u32(stage) + 2 * 32 * 64 + pp * 64;
+              const uint32_t pph = (pp >> 1) & 3;
+              sts128(prow + ((static_cast<uint32_t>(2 * h) ^ pph) << 4), pm[0], pm[1], pm[2], pm[3]);
+              sts128(prow + ((static_cast<uint32_t>(2 * h + 1) ^ pph) << 4), pm[4], pm[5], pm[6], pm[7]);
+            }
+            sts128(row0 + ((static_cast<uint32_t>(2 * h) ^ phase) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
+            sts128(row0 + ((static_cast<uint32_t>(2 * h + 1) ^ phase) << 4), pk0[4], pk0[5], pk0[6], pk0[7]);
+            sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(2 * h) ^ phase) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
+            sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(2 * h + 1) ^ phase) << 4), pk1[4], pk1[5], pk1[6], pk1[7]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out != nullptr) tma_store_4d(&tmOut, stage, p.out_choff, xw, y, sg.n);
+            tma_store_4d(&tmPool, stage + 2 * 32 * 64, 0, xw >> 1, y >> 1, sg.n);
+            bulk_commit();
+          }
+        }
       }
       opc += sg.npairs;
     }
+    if constexpr (EPI2 == EPI_POOL_SKIP) {
+      if (lane == 0) bulk_wait_read<0>();  // staging must stay valid until the last stores have read it
+    }
+#ifdef SCV_ROWS_PROF
+    if ((p.dbg & 32) && blockIdx.x < 3 && lane == 0 && q == 0)
+      printf("[fused prof] cta %d epilogue B group %d: total %lld cyc over %u pairs: wait acc2_full %lld\n", blockIdx.x, g,
+             ROWS_CLOCK() - tb_begin, tb_n, tb_wait);
+#endif
   }
 
   tc_fence_before();

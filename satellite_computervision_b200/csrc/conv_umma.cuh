@@ -1073,7 +1073,7 @@ cudaError_t conv_init_attributes();
 // conv_fused.cu
 cudaError_t conv_fused_launch(const ConvLaunch& L, cudaStream_t stream);
 cudaError_t conv_fused_init_attributes();
-int conv_fused_max_clusters(size_t smem);
+int conv_fused_max_clusters(size_t smem, int epi2);
 // conv_rows.cu
 cudaError_t conv_rows_launch(const ConvLaunch& L, cudaStream_t stream);
 cudaError_t conv_rows_init_attributes();

@@ -931,26 +931,42 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
               Ln.slab == 3 ? 2 : (Ln.slab ? Ln.nacc : 1), Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
-  // Fuse decoder_0/conv0 -> decoder_0/conv1 + head into one cluster launch (conv_fused.cuh) when both run in the row
-  // kernel on 384-pixel rows: the 32-channel intermediate then never goes to HBM.  Bit-identical to the two launches.
-  for (size_t i = 0; i + 1 < a.layers.size() && env_int("SCV_FUSE", 1); ++i) {
+  // Fuse 32-channel conv pairs of the 384-pixel level into one cluster launch (conv_fused.cuh) when both halves run in
+  // the row kernel: decoder_0/conv0 -> conv1 + head (bit 0 of SCV_FUSE, on) and encoder_0/conv0 -> conv1 + pool + skip
+  // (bit 1, off: correct and bit-identical, but slower than its two launches -- 19.4 vs 14.3 ms -- because its single
+  // conv-1 epilogue group cannot feed conv 2; cycle accounting in profiles/r02_fused_kernel.md).  The 32-channel
+  // intermediate never goes to HBM.  Bit-identical to the two launches.
+  const int fuse = env_int("SCV_FUSE", 1);
+  for (size_t i = 0; i + 1 < a.layers.size() && fuse; ++i) {
     const LayerDef &l1 = a.layers[i], &l2 = a.layers[i + 1];
     ConvLaunch &A = pl->launches[i], &Bn = pl->launches[i + 1];
-    if (A.slab != 2 || Bn.slab != 2 || l1.epi != EPI_STORE || l2.epi != EPI_HEAD || l1.cout != 32 || l2.cout != 32 ||
-        l1.cin_pad != 64 || l1.KC != 64 || l2.cin_pad != 32 || l2.in_buf != l1.out_buf || l1.level != 0 || l2.level != 0 ||
-        W != kF2Cluster * kRowsPx || (H & 1))
+    if (A.slab != 2 || Bn.slab != 2 || l1.epi != EPI_STORE || l1.cout != 32 || l2.cout != 32 || l2.cin_pad != 32 ||
+        l2.KC != 32 || l2.in_buf != l1.out_buf || l1.level != 0 || l2.level != 0 || W != kF2Cluster * kRowsPx || (H & 1))
       continue;
-    const size_t smem = fused_smem_bytes(64, a.cfg.nclasses);
+    const bool tail = l2.epi == EPI_HEAD && l1.KC == 64 && l1.cin_pad == 64 && (fuse & 1);
+    const bool head = l2.epi == EPI_POOL_SKIP && l1.KC == 8 && A.KC == 16 && (fuse & 2);
+    if (!tail && !head) continue;
+    const size_t smem = fused_smem_bytes(A.KC, l2.epi, a.cfg.nclasses);
     if (smem > 227 * 1024) continue;
-    const int ncl = conv_fused_max_clusters(smem);
+    const int ncl = conv_fused_max_clusters(smem, l2.epi);
     if (ncl < 8) continue;  // cluster launch not available / too few co-resident clusters: keep the two launches
     A.slab = 5;
+    A.EPI = l2.epi;
     A.tmB2 = Bn.tmB;
+    A.tmOut = Bn.tmOut;
+    A.tmPool = Bn.tmPool;
     A.p.bias2 = l2.d_bias;
     A.p.head_w = Bn.p.head_w;
     A.p.head_b = Bn.p.head_b;
     A.p.ncls = Bn.p.ncls;
     A.p.logits = Bn.p.logits;
+    A.p.out = Bn.p.out;
+    A.p.out_pitch = Bn.p.out_pitch;
+    A.p.out_choff = Bn.p.out_choff;
+    A.p.pool_out = Bn.p.pool_out;
+    A.p.pool_pitch = Bn.p.pool_pitch;
+    A.p.skip_s = Bn.p.skip_s;
+    A.p.skip_t = Bn.p.skip_t;
     A.smem = smem;
     A.grid = kF2Cluster * (int)std::min<long long>(ncl, (long long)B * (H / 2));
     Bn.slab = -1;
@@ -991,7 +1007,7 @@ static int run_layers(scv_engine* e, Plan* pl, int tile_off, int side, cudaStrea
     ConvLaunch L = pl->launches[i];
     const LayerDef& l = a.layers[i];
     if (l.in_buf == a.x0_buf) L.p.n_in_off = tile_off;
-    if (l.epi == EPI_HEAD || L.slab == 5) L.p.logits = e->d_logits_all + (size_t)tile_off * side * side * a.cfg.nclasses;
+    if (l.epi == EPI_HEAD || (L.slab == 5 && L.EPI == EPI_HEAD)) L.p.logits = e->d_logits_all + (size_t)tile_off * side * side * a.cfg.nclasses;
     if (L.slab < 0) continue;  // folded into the previous (fused) launch
     cudaError_t err = conv_launch(L, s);
     if (err != cudaSuccess)

@@ -2,8 +2,8 @@
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_fused.py -m gpu -q -x 2>&1 | tail -5
 B="python bench.py --steps 3 --warmup 2 --no-cpu-baseline --profile-layers"
-SCV_FUSE=1 $B > gpurun_out/r02_u_fuse1.json 2> gpurun_out/r02_u_fuse1.err
-python - gpurun_out/r02_u_fuse1.json <<'P'
+SCV_FUSE=3 $B > gpurun_out/r02_v_fuse3.json 2> gpurun_out/r02_v_fuse3.err
+python - gpurun_out/r02_v_fuse3.json <<'P'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
