@@ -29,10 +29,17 @@ namespace scv {
 
 constexpr int kF2Issuers1 = 2, kF2Issuers2 = 2;                   // issuer warps per conv (taking turns: a single issuer
                                                                   // spends > 1000 cycles per row on waits and commits)
-// epilogue warpgroups per conv: the decoder tail (fused head) splits them 2 + 2; the encoder pair, whose second
-// epilogue pools, applies the skip affine and stores two tensors, 1 + 3
-__host__ __device__ constexpr int f2_groups1(int epi2) { return epi2 == EPI_POOL_SKIP ? 1 : 2; }
-__host__ __device__ constexpr int f2_groups2(int epi2) { return epi2 == EPI_POOL_SKIP ? 3 : 2; }
+// epilogue warpgroups per conv (four in total).  Conv 1's epilogue -- whose proxy fence + arrive is what conv 2 waits
+// for -- gets three of them in the decoder tail (fused head: light second epilogue) and two in the encoder pair (pool +
+// skip + two TMA stores).  Measured: decoder 13.5 (2 + 2) -> 13.3 ms (3 + 1); encoder 19.4 (1 + 3) -> 14.1 ms (2 + 2).
+#ifndef SCV_F2_G1_HEAD
+#define SCV_F2_G1_HEAD 3
+#endif
+#ifndef SCV_F2_G1_POOL
+#define SCV_F2_G1_POOL 2
+#endif
+__host__ __device__ constexpr int f2_groups1(int epi2) { return epi2 == EPI_POOL_SKIP ? SCV_F2_G1_POOL : SCV_F2_G1_HEAD; }
+__host__ __device__ constexpr int f2_groups2(int epi2) { return 4 - f2_groups1(epi2); }
 constexpr int kF2Issuer2Warp = 1 + kF2Issuers1;                   // warp 0: TMA, 1..2: conv-1 issuers, 3..4: conv-2 issuers
 constexpr int kF2FirstEpi1 = 8;                                   // warps 5..7 idle (TMEM lane quadrant == warp & 3)
 constexpr int kF2Threads = 32 * (kF2FirstEpi1 + 4 * 4);           // 768: four epilogue warpgroups in total
@@ -495,7 +502,10 @@ __global__ void __launch_bounds__(kF2Threads, 1)
           }
         }
         const long long c4 = ROWS_CLOCK();
-        fence_proxy_async_all();  // generic-proxy stores (local and remote) -> visible to the UMMAs that read the slab
+        // generic-proxy stores (local and remote) -> visible to the UMMAs that read the slab.  (A CTA-scoped fence for
+        // the 126 threads without remote stores measured the same: the fence waits for the shared stores, which compete
+        // with the UMMA operand fetch.)
+        fence_proxy_async_all();
         mbar_arrive(&ring_full[rs]);
         if (edge_l) {
           if (xs > 0) mbar_arrive_remote(mapa_shared(smem_u32(&ring_full[rs]), xs - 1));

@@ -931,12 +931,11 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
               Ln.slab == 3 ? 2 : (Ln.slab ? Ln.nacc : 1), Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
-  // Fuse 32-channel conv pairs of the 384-pixel level into one cluster launch (conv_fused.cuh) when both halves run in
-  // the row kernel: decoder_0/conv0 -> conv1 + head (bit 0 of SCV_FUSE, on) and encoder_0/conv0 -> conv1 + pool + skip
-  // (bit 1, off: correct and bit-identical, but slower than its two launches -- 19.4 vs 14.3 ms -- because its single
-  // conv-1 epilogue group cannot feed conv 2; cycle accounting in profiles/r02_fused_kernel.md).  The 32-channel
-  // intermediate never goes to HBM.  Bit-identical to the two launches.
-  const int fuse = env_int("SCV_FUSE", 1);
+  // Fuse the two 32-channel conv pairs of the 384-pixel level into one cluster launch each (conv_fused.cuh) when both
+  // halves run in the row kernel: decoder_0/conv0 -> conv1 + head (bit 0 of SCV_FUSE) and encoder_0/conv0 -> conv1 +
+  // pool + skip (bit 1).  The 32-channel intermediates never go to HBM.  Bit-identical to the two launches.  Full
+  // scene: 125.0 ms unfused, 122.9-123.4 with the decoder tail fused, 121.6-121.9 with both (tools/r02_exp21.sh).
+  const int fuse = env_int("SCV_FUSE", 3);
   for (size_t i = 0; i + 1 < a.layers.size() && fuse; ++i) {
     const LayerDef &l1 = a.layers[i], &l2 = a.layers[i + 1];
     ConvLaunch &A = pl->launches[i], &Bn = pl->launches[i + 1];
