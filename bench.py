@@ -384,7 +384,7 @@ def main():
     value = mp_scene / (ms_step / 1e3)
 
     # ---------------- end-to-end leg (host buffers through the C-ABI)
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(1, args.warmup)):  # the same W as the device-resident leg (PCIe / copy engines warm up too)
         step_e2e()
     barrier()
     t0 = time.perf_counter()

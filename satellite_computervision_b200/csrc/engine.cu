@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <memory>
 #include <string>
@@ -1700,9 +1701,18 @@ static cudaEvent_t slot_event(std::vector<cudaEvent_t>& pool, size_t i) {
 
 // Enqueues one scene on slot `sl` (H2D per tile row on the copy stream, K1 / network / K4 per super-batch on the
 // compute stream, D2H of every completed tile row on the third stream) and returns without waiting.
+static double host_now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* hwc, int dtype, int H, int W, int C,
                               const scv_tiling* tiling, const scv_norm* norm, const scv_mosaic_opts* opts,
                               void* out_prob, uint8_t* out_mask, bool may_register) {
+  const bool trace = env_int("SCV_HOST_TRACE", 0) != 0;
+  const double tr0 = trace ? host_now_ms() : 0.0;
+  double tr1 = 0, tr2 = 0;
   MosaicGeom g;
   SCV_TRY(mosaic_geom(e, H, W, tiling, opts, &g));
   reset_timing(e);
@@ -1773,11 +1783,13 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
     if (!ev) rc = fail(SCV_ERR_CUDA, "cudaEventCreate failed");
     else HOST_TRY(cudaEventRecord(ev, e->h2d));
   };
+  if (trace) tr1 = host_now_ms();
   const bool pinned_in = host_is_pinned((const uint8_t*)hwc + (size_t)src_row0 * row_bytes);
   const bool pinned_out = host_is_pinned((uint8_t*)out_prob + (size_t)dst_row0 * W * osz);
   if (pinned_in && (!acc || pinned_out))
     for (; rows_uploaded < ntr && rc == SCV_OK; ++rows_uploaded) upload_tile_row(g.r_first + rows_uploaded);
 
+  if (trace) tr2 = host_now_ms();
   TileJob job{};
   fill_mosaic_job(&job, g, dtype, W, C, norm, opts, force_scalar, e->d_origins);
   job.d_src = sl.d_scene;
@@ -1845,6 +1857,9 @@ static int submit_host_mosaic(scv_engine* e, scv_engine::Slot& sl, const void* h
   if (rc == SCV_OK && pending_ev) download_rows(pending_rows, pending_ev);
   e->ev_host_end = new_event(e, e->d2h);
 #undef HOST_TRY
+  if (trace)
+    fprintf(stderr, "[scv host trace dev %d] setup %.3f ms, H2D enqueue %.3f ms, kernels + D2H enqueue %.3f ms\n", e->device,
+            tr1 - tr0, tr2 - tr1, host_now_ms() - tr2);
   sl.busy = true;
   cudaEventRecord(sl.compute_done, e->stream);
   cudaEventRecord(sl.d2h_done, e->d2h);
@@ -1900,12 +1915,20 @@ int scv_stream_wait(scv_engine* e, int ticket) {
 int scv_predict_mosaic_ex(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
                           const scv_norm* norm, const scv_mosaic_opts* opts, void* out_prob, uint8_t* out_mask) {
   DeviceGuard guard;
+  const bool trace = env_int("SCV_HOST_TRACE", 0) != 0;
+  const double t0 = trace ? host_now_ms() : 0.0;
   SCV_TRY(host_args_check(e, hwc, dtype, C, opts, out_prob));
   for (auto& sl : e->slots) SCV_TRY(slot_wait(e, sl));  // a synchronous call does not overtake streamed scenes
   scv_engine::Slot& sl = e->slots[0];
+  const double t1 = trace ? host_now_ms() : 0.0;
   SCV_TRY(submit_host_mosaic(e, sl, hwc, dtype, H, W, C, tiling, norm, opts, out_prob, out_mask, true));
   sl.ticket = -1;
-  return slot_wait(e, sl);
+  const double t2 = trace ? host_now_ms() : 0.0;
+  const int rc = slot_wait(e, sl);
+  if (trace)
+    fprintf(stderr, "[scv host trace dev %d] call: entry %.3f ms, submit %.3f ms, wait %.3f ms\n", e->device, t1 - t0, t2 - t1,
+            host_now_ms() - t2);
+  return rc;
 }
 
 int scv_predict_mosaic(scv_engine* e, const void* hwc, int dtype, int H, int W, int C, const scv_tiling* tiling,
