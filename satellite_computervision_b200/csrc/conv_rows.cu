@@ -29,7 +29,7 @@ cudaError_t rows_attr() {
 }  // namespace
 
 cudaError_t conv_rows_launch(const ConvLaunch& L, cudaStream_t s) {
-  if (L.p.ntaps != 9 || L.p.W % kRowsPx || (L.p.H & 1)) return cudaErrorInvalidValue;
+  if (L.p.ntaps != 9 || (L.p.W & 1) || (L.p.H & 1)) return cudaErrorInvalidValue;
   if (L.KC == 16 && L.BN == 32) return rows_epi<16, 32>(L, s);  // first layer: 8 stored channels, zero-filled to 16 by TMA
   if (L.KC == 16 && L.BN == 64) return rows_epi<16, 64>(L, s);
   if (L.KC == 32 && L.BN == 32) return rows_epi<32, 32>(L, s);

@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(rows_threads(COUT, EPI), 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int XS = p.W / kRowsPx, H2 = p.H >> 1;
+  const int XS = (p.W + kRowsPx - 1) / kRowsPx, H2 = p.H >> 1;  // the last strip may be partial: TMA zero-fills its
+                                                                // loads and clips its stores at the image border
   const long long P = static_cast<long long>(p.N) * XS * H2;
   const long long p0 = P * blockIdx.x / gridDim.x, p1 = P * (blockIdx.x + 1) / gridDim.x;
 
@@ -450,8 +451,8 @@ __global__ void __launch_bounds__(rows_threads(COUT, EPI), 1)
         const int y = sg.y0 + 2 * u;
         if constexpr (EPI == EPI_HEAD) {
           if (!(p.dbg & 1)) {
-            epilogue_head<COUT>(p, taddr, 0, 0, xw + lane, y, sg.n, true, 0, s_bias, s_extra);
-            epilogue_head<COUT>(p, taddr + COUT, 0, 0, xw + lane, y + 1, sg.n, true, 0, s_bias, s_extra);
+            epilogue_head<COUT>(p, taddr, 0, 0, xw + lane, y, sg.n, xw + lane < p.W, 0, s_bias, s_extra);
+            epilogue_head<COUT>(p, taddr + COUT, 0, 0, xw + lane, y + 1, sg.n, xw + lane < p.W, 0, s_bias, s_extra);
           }
           if (!(p.dbg & 2)) {
 #pragma unroll
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(rows_threads(COUT, EPI), 1)
             fence_proxy_async();
             __syncwarp();
             t_fence += ROWS_CLOCK() - tf0;
-            if (lane == 0 && !(p.dbg & 16)) {
+            if (lane == 0 && !(p.dbg & 16) && xw < p.W) {  // (a warp wholly beyond a partial strip's edge stores nothing)
               if (p.out != nullptr) tma_store_4d(&tmOut, stage, p.out_choff + b * 32, xw, y, sg.n);
               if constexpr (EPI == EPI_POOL_SKIP) tma_store_4d(&tmPool, stage + 2 * 32 * 64, b * 32, xw >> 1, y >> 1, sg.n);
               bulk_commit();

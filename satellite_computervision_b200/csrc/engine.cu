@@ -704,7 +704,14 @@ static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* 
 // tile's result does not depend on how many tiles ran with it.
 static bool plan_rows(const LayerDef& l, int h, int w, int ncls, int* nslab) {
   if (!env_int("SCV_ROWS", 1)) return false;
-  if (l.kind != L_CONV3 || w % kRowsPx || (h & 1)) return false;
+  if (l.kind != L_CONV3 || (h & 1) || (w & 1)) return false;
+  if (w % kRowsPx) {
+    // partial last strip (192-pixel rows = 1.5 strips; SCV_ROWS_PARTIAL=1): supported -- TMA zero-fills the loads
+    // and clips the stores -- and bit-identical to the 8x16-tile kernels, but measured no faster on the Cout = 64
+    // layers at 192 x 192 (enc1.c2 4.92 vs 4.93 ms, dec1.c2 4.42 vs 4.45 ms: 25 % of the M lanes idle), so off
+    const int strips = (w + kRowsPx - 1) / kRowsPx;
+    if (!env_int("SCV_ROWS_PARTIAL", 0) || w < kRowsPx || 10 * w < 7 * strips * kRowsPx) return false;
+  }
   const bool first = l.KC == 8 && l.d_w16 != nullptr && env_int("SCV_ROWS_FIRST", 1);  // 8 stored channels read as 16
   if (l.KC != 32 && l.KC != 64 && !first) return false;
   if (l.ntotal != l.cout || (l.cout != 32 && l.cout != 64)) return false;
@@ -749,7 +756,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     L->BN = l.cout;
     L->nacc = rows_epi_groups(l.cout, l.epi);
     p.TW = kRowsPx, p.TH = 1, p.TN = 1;
-    p.tiles_x = w / kRowsPx;
+    p.tiles_x = (w + kRowsPx - 1) / kRowsPx;
     p.tiles_y = h;
     p.tiles_n = B;
     p.n_tiles_n = 1;

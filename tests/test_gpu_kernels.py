@@ -48,11 +48,15 @@ ROWS_CASES = [
     (2, 22, 256, 64, 64, 3),      # uneven split over 3 CTAs: segments start mid-image
     (1, 36, 128, 128, 32, 2),     # two chunks per row, streaming
     (3, 18, 128, 16, 64, 2),      # KC=16 is not a row-kernel shape: must still be right (slab / tile path)
+    (2, 12, 192, 64, 64, 0),      # 1.5 strips: the second strip is partial (TMA zero-fills its loads, clips its stores)
+    (1, 16, 192, 32, 64, 2),
+    (1, 6, 320, 64, 32, 0),       # 2.5 strips
 ]
 
 
 @pytest.mark.parametrize('N,H,W,Cin,Cout,grid', ROWS_CASES)
 def test_conv3x3_rows_kernel_matches_torch(N, H, W, Cin, Cout, grid, monkeypatch):
+    monkeypatch.setenv('SCV_ROWS_PARTIAL', '1')  # widths that are not a multiple of 128 stay in the row kernel
     if grid:
         monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
     rng = np.random.default_rng(N * 1000 + H + W + Cin + Cout)
@@ -67,8 +71,9 @@ def test_conv3x3_rows_kernel_matches_torch(N, H, W, Cin, Cout, grid, monkeypatch
 
 
 @pytest.mark.parametrize('N,H,W,Cin,Cout,grid', [(2, 8, 128, 32, 32, 0), (1, 12, 256, 64, 64, 0), (2, 36, 128, 32, 32, 1),
-                                                 (2, 20, 256, 32, 64, 3)])
+                                                 (2, 20, 256, 32, 64, 3), (2, 12, 192, 64, 64, 0), (1, 24, 192, 32, 64, 2)])
 def test_rows_kernel_fused_maxpool(N, H, W, Cin, Cout, grid, monkeypatch):
+    monkeypatch.setenv('SCV_ROWS_PARTIAL', '1')
     if grid:
         monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
     rng = np.random.default_rng(17)
@@ -90,6 +95,15 @@ def test_rows_kernel_equals_slab_kernel_bitwise(monkeypatch):
     monkeypatch.setenv('SCV_ROWS', '0')
     other = G.conv3x3_device(x, k, b)
     assert np.array_equal(rows, other)
+    # ... and with a partial last strip (192-pixel rows, the Cout = 64 layers of the 192 x 192 level)
+    monkeypatch.delenv('SCV_ROWS')
+    monkeypatch.setenv('SCV_ROWS_PARTIAL', '1')
+    x2 = rng.standard_normal((2, 16, 192, 64)).astype(np.float32)
+    k2 = (rng.standard_normal((3, 3, 64, 64)) / 24).astype(np.float32)
+    b2 = rng.standard_normal(64).astype(np.float32) * 0.1
+    rows2 = G.conv3x3_device(x2, k2, b2)
+    monkeypatch.setenv('SCV_ROWS', '0')
+    assert np.array_equal(rows2, G.conv3x3_device(x2, k2, b2))
 
 
 @pytest.mark.parametrize('N,H,W,Cin,Cout', CONV_CASES)
