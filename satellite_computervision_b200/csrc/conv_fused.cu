@@ -8,7 +8,7 @@ template <int KC1, int EPI2>
 cudaError_t fused_launch_t(const ConvLaunch& L, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(L.grid));
-  cfg.blockDim = dim3(kF2Threads);
+  cfg.blockDim = dim3(f2_threads(EPI2));
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -33,7 +33,7 @@ cudaError_t conv_fused_launch(const ConvLaunch& L, cudaStream_t s) {
 int conv_fused_max_clusters(size_t smem, int epi2) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kF2Cluster * 64);
-  cfg.blockDim = dim3(kF2Threads);
+  cfg.blockDim = dim3(f2_threads(epi2));
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

@@ -29,27 +29,33 @@ namespace scv {
 
 constexpr int kF2Issuers1 = 2, kF2Issuers2 = 2;                   // issuer warps per conv (taking turns: a single issuer
                                                                   // spends > 1000 cycles per row on waits and commits)
-// epilogue warpgroups per conv (four in total).  Conv 1's epilogue -- whose proxy fence + arrive is what conv 2 waits
-// for -- gets three of them in the decoder tail (fused head: light second epilogue) and two in the encoder pair (pool +
-// skip + two TMA stores).  Measured: decoder 13.5 (2 + 2) -> 13.3 ms (3 + 1); encoder 19.4 (1 + 3) -> 14.1 ms (2 + 2).
+// Epilogue warpgroups (four per kernel, 768 threads).  The decoder tail (fused head) gives three to conv 1 -- whose
+// proxy fence + arrive is what conv 2 waits for -- and one to the light head epilogue (13.5 ms with 2 + 2 -> 13.3 with
+// 3 + 1); the encoder pair, whose second epilogue pools, applies the skip affine and stores two tensors, splits 2 + 2
+// (19.4 ms with 1 + 3 -> 14.1).  The epilogues work on 8 channels at a time (61-72 registers), so six groups (1024
+// threads, -DSCV_F2_GROUPS_POOL=6) fit without spills -- measured 13.9 vs 14.0 ms: warps are not what it lacks.
 #ifndef SCV_F2_G1_HEAD
 #define SCV_F2_G1_HEAD 3
 #endif
 #ifndef SCV_F2_G1_POOL
 #define SCV_F2_G1_POOL 2
 #endif
+#ifndef SCV_F2_GROUPS_POOL
+#define SCV_F2_GROUPS_POOL 4
+#endif
+__host__ __device__ constexpr int f2_groups(int epi2) { return epi2 == EPI_POOL_SKIP ? SCV_F2_GROUPS_POOL : 4; }
 __host__ __device__ constexpr int f2_groups1(int epi2) { return epi2 == EPI_POOL_SKIP ? SCV_F2_G1_POOL : SCV_F2_G1_HEAD; }
-__host__ __device__ constexpr int f2_groups2(int epi2) { return 4 - f2_groups1(epi2); }
+__host__ __device__ constexpr int f2_groups2(int epi2) { return f2_groups(epi2) - f2_groups1(epi2); }
 constexpr int kF2Issuer2Warp = 1 + kF2Issuers1;                   // warp 0: TMA, 1..2: conv-1 issuers, 3..4: conv-2 issuers
 constexpr int kF2FirstEpi1 = 8;                                   // warps 5..7 idle (TMEM lane quadrant == warp & 3)
-constexpr int kF2Threads = 32 * (kF2FirstEpi1 + 4 * 4);           // 768: four epilogue warpgroups in total
+__host__ __device__ constexpr int f2_threads(int epi2) { return 32 * (kF2FirstEpi1 + 4 * f2_groups(epi2)); }
 constexpr int kF2R = 8;                                           // row accumulators per conv: 8 x 32 columns = 256
 constexpr int kF2RP = kF2R / 2;
 constexpr int kF2InSlabs = 3;                                     // conv-1 input slabs (two rows of 130 px x 64 ch)
 constexpr int kF2Ring = 4;                                        // conv-1 -> conv-2 slabs (two rows of 130 px x 32 ch)
 constexpr int kF2Cluster = 3;                                     // strips per image row
 static_assert(kF2FirstEpi1 % 4 == 0, "epilogue warps must start on a TMEM quadrant boundary");
-static_assert(kF2RP >= 3 && kF2RP >= kF2Issuers1 && kF2RP >= kF2Issuers2, "accumulator reuse distance (<= 3 groups per conv)");
+static_assert(kF2RP >= 4 && kF2RP >= kF2Issuers1 && kF2RP >= kF2Issuers2, "accumulator reuse distance (<= 4 groups per conv)");
 static_assert(kF2Issuer2Warp + kF2Issuers2 <= kF2FirstEpi1 && kF2Ring >= kF2Issuers2, "warp layout / ring depth");
 
 __host__ __device__ inline size_t fused_smem_bytes(int KC1, int epi2, int ncls) {
@@ -142,7 +148,7 @@ __device__ __forceinline__ RowsPiece rows_piece_r(uint32_t base, int j, int npai
 // TMA boxes).  Conv 2 is 32 -> 32; EPI2 = EPI_HEAD (decoder tail: fused 1x1 head -> logits) or EPI_POOL_SKIP (encoder
 // pair: 2x2 max-pool + skip affine, two TMA-stored outputs).
 template <int KC1, int EPI2>
-__global__ void __launch_bounds__(kF2Threads, 1)
+__global__ void __launch_bounds__(f2_threads(EPI2), 1)
     conv_fused2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                        const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut,
                        const __grid_constant__ CUtensorMap tmPool, const ConvParams p) {
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(kF2Threads, 1)
     tmem_relinquish();
   }
   if (warp >= kF2FirstEpi1) {
-    const int t = threadIdx.x - 32 * kF2FirstEpi1, nt = kF2Threads - 32 * kF2FirstEpi1;
+    const int t = threadIdx.x - 32 * kF2FirstEpi1, nt = f2_threads(EPI2) - 32 * kF2FirstEpi1;
     for (int i = t; i < COUT; i += nt) {
       s_bias1[i] = p.bias[i];
       s_bias2[i] = p.bias2[i];
@@ -436,14 +442,18 @@ __global__ void __launch_bounds__(kF2Threads, 1)
         const uint32_t slab = ring_u32 + rs * STRIDE2;
         const uint32_t nb_l = (edge_l && xs > 0) ? mapa_shared(slab, xs - 1) : 0u;
         const uint32_t nb_r = (edge_r && xs + 1 < kF2Cluster) ? mapa_shared(slab, xs + 1) : 0u;
+        // 8 channels = one 16-byte chunk of a pixel row per step (keeps the epilogue within 64 registers, which is what
+        // lets six epilogue warpgroups share the register file)
+        // a slab is laid out like a TMA-written SWIZZLE_64B box: 16-byte chunk c of the pixel row at byte offset o
+        // sits at o + ((c ^ ((o >> 7) & 3)) << 4)  (slabs are 1024-byte aligned)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r0[16], r1[16];
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t r0[8], r1[8];
           const long long c3 = ROWS_CLOCK();
-          tmem_ld16(taddr + h * 16, r0);
-          tmem_ld16(taddr + COUT + h * 16, r1);
+          tmem_ld8(taddr + c8 * 8, r0);
+          tmem_ld8(taddr + COUT + c8 * 8, r1);
           tmem_ld_wait();
-          if (h == 1) {  // everything read: zero both accumulators and hand them back
+          if (c8 == 3) {  // everything read: zero both accumulators and hand them back
 #pragma unroll
             for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
             tmem_st_wait();
@@ -451,11 +461,11 @@ __global__ void __launch_bounds__(kF2Threads, 1)
             mbar_arrive(&acc1_empty[slot]);
           }
           ta_ld += ROWS_CLOCK() - c3;
-          float bias[16];
-          lds16(s_bias1 + h * 16, bias);
-          uint32_t pk0[8], pk1[8];
+          float bias[8];
+          lds8(s_bias1 + c8 * 8, bias);
+          uint32_t pk0[4], pk1[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             pk0[j] = pack_bf16x2(__uint_as_float(r0[2 * j]) + bias[2 * j], __uint_as_float(r0[2 * j + 1]) + bias[2 * j + 1]);
             pk1[j] = pack_bf16x2(__uint_as_float(r1[2 * j]) + bias[2 * j], __uint_as_float(r1[2 * j + 1]) + bias[2 * j + 1]);
             if (p.relu) {
@@ -465,30 +475,21 @@ __global__ void __launch_bounds__(kF2Threads, 1)
             if (!in_a) pk0[j] = 0u;
             if (!in_b) pk1[j] = 0u;
           }
-          // a slab is laid out like a TMA-written SWIZZLE_64B box: 16-byte chunk c of the pixel row at byte offset o
-          // sits at o + ((c ^ ((o >> 7) & 3)) << 4)  (slabs are 1024-byte aligned)
-          auto put_px = [&](uint32_t slab_addr, uint32_t off, const uint32_t (&v)[8], bool remote) {
-            const uint32_t phs = (off >> 7) & 3;
-            const uint32_t a0 = slab_addr + off + ((static_cast<uint32_t>(2 * h) ^ phs) << 4);
-            const uint32_t a1 = slab_addr + off + ((static_cast<uint32_t>(2 * h + 1) ^ phs) << 4);
-            if (remote) {
-              st_cluster128(a0, v[0], v[1], v[2], v[3]);
-              st_cluster128(a1, v[4], v[5], v[6], v[7]);
-            } else {
-              sts128(a0, v[0], v[1], v[2], v[3]);
-              sts128(a1, v[4], v[5], v[6], v[7]);
-            }
+          auto put_px = [&](uint32_t slab_addr, uint32_t off, const uint32_t (&v)[4], bool remote) {
+            const uint32_t a0 = slab_addr + off + ((static_cast<uint32_t>(c8) ^ ((off >> 7) & 3)) << 4);
+            if (remote) st_cluster128(a0, v[0], v[1], v[2], v[3]);
+            else sts128(a0, v[0], v[1], v[2], v[3]);
           };
           put_px(slab, px_off, pk0, false);
           put_px(slab, ROW2 + px_off, pk1, false);
-          const uint32_t zero8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          const uint32_t zero4[4] = {0u, 0u, 0u, 0u};
           if (edge_l) {  // strip pixel 0: the left neighbour's halo pixel 129, or this CTA's own (zero) halo pixel 0
             if (xs > 0) {
               put_px(nb_l, (kRowsSlabPx - 1) * ROWB2, pk0, true);
               put_px(nb_l, ROW2 + (kRowsSlabPx - 1) * ROWB2, pk1, true);
             } else {
-              put_px(slab, 0, zero8, false);
-              put_px(slab, ROW2, zero8, false);
+              put_px(slab, 0, zero4, false);
+              put_px(slab, ROW2, zero4, false);
             }
           }
           if (edge_r) {
@@ -496,8 +497,8 @@ __global__ void __launch_bounds__(kF2Threads, 1)
               put_px(nb_r, 0, pk0, true);
               put_px(nb_r, ROW2, pk1, true);
             } else {
-              put_px(slab, (kRowsSlabPx - 1) * ROWB2, zero8, false);
-              put_px(slab, ROW2 + (kRowsSlabPx - 1) * ROWB2, zero8, false);
+              put_px(slab, (kRowsSlabPx - 1) * ROWB2, zero4, false);
+              put_px(slab, ROW2 + (kRowsSlabPx - 1) * ROWB2, zero4, false);
             }
           }
         }
@@ -569,26 +570,26 @@ __global__ void __launch_bounds__(kF2Threads, 1)
           __syncwarp();
           const uint32_t row0 = smem_u32(stage) + lane * 64;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int col = h * 16;
-            uint32_t r0[16], r1[16];
-            tmem_ld16(taddr + col, r0);
-            tmem_ld16(taddr + COUT + col, r1);
+          for (int c8 = 0; c8 < 4; ++c8) {  // 8 channels = one 16-byte chunk of every staging row per step
+            const int col = c8 * 8;
+            uint32_t r0[8], r1[8];
+            tmem_ld8(taddr + col, r0);
+            tmem_ld8(taddr + COUT + col, r1);
             tmem_ld_wait();
-            if (h == 1) {
+            if (c8 == 3) {
 #pragma unroll
               for (int c = 0; c < 2 * COUT; c += 32) tmem_st32_zero(taddr + c);
               tmem_st_wait();
               tc_fence_before();
               mbar_arrive(&acc2_empty[slot]);
             }
-            float bias[16], sc[16], sh[16];
-            lds16(s_bias2 + col, bias);
-            lds16(s_head + col, sc);
-            lds16(s_head + COUT + col, sh);
-            uint32_t pk0[8], pk1[8], pm[8];
+            float bias[8], sc[8], sh[8];
+            lds8(s_bias2 + col, bias);
+            lds8(s_head + col, sc);
+            lds8(s_head + COUT + col, sh);
+            uint32_t pk0[4], pk1[4], pm[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               float a0 = __uint_as_float(r0[2 * j]) + bias[2 * j], a1 = __uint_as_float(r0[2 * j + 1]) + bias[2 * j + 1];
               float c0 = __uint_as_float(r1[2 * j]) + bias[2 * j], c1 = __uint_as_float(r1[2 * j + 1]) + bias[2 * j + 1];
               if (p.relu) a0 = fmaxf(a0, 0.f), a1 = fmaxf(a1, 0.f), c0 = fmaxf(c0, 0.f), c1 = fmaxf(c1, 0.f);
@@ -600,14 +601,10 @@ __global__ void __launch_bounds__(kF2Threads, 1)
             if (!(lane & 1)) {
               const uint32_t pp = lane >> 1;  // pooled pixel of this warp
               const uint32_t prow = smem_u32(stage) + 2 * 32 * 64 + pp * 64;
-              const uint32_t pph = (pp >> 1) & 3;
-              sts128(prow + ((static_cast<uint32_t>(2 * h) ^ pph) << 4), pm[0], pm[1], pm[2], pm[3]);
-              sts128(prow + ((static_cast<uint32_t>(2 * h + 1) ^ pph) << 4), pm[4], pm[5], pm[6], pm[7]);
+              sts128(prow + ((static_cast<uint32_t>(c8) ^ ((pp >> 1) & 3)) << 4), pm[0], pm[1], pm[2], pm[3]);
             }
-            sts128(row0 + ((static_cast<uint32_t>(2 * h) ^ phase) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
-            sts128(row0 + ((static_cast<uint32_t>(2 * h + 1) ^ phase) << 4), pk0[4], pk0[5], pk0[6], pk0[7]);
-            sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(2 * h) ^ phase) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
-            sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(2 * h + 1) ^ phase) << 4), pk1[4], pk1[5], pk1[6], pk1[7]);
+            sts128(row0 + ((static_cast<uint32_t>(c8) ^ phase) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
+            sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(c8) ^ phase) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
           }
           fence_proxy_async();
           __syncwarp();

@@ -139,6 +139,15 @@ __device__ __forceinline__ void lds16(const float* src, float (&dst)[16]) {
                  : "r"(a + 16 * j));
 }
 
+__device__ __forceinline__ void lds8(const float* src, float (&dst)[8]) {
+  const uint32_t a = smem_u32(src);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(dst[4 * j + 0]), "=f"(dst[4 * j + 1]), "=f"(dst[4 * j + 2]), "=f"(dst[4 * j + 3])
+                 : "r"(a + 16 * j));
+}
+
 __device__ __forceinline__ void lds32(const float* src, float (&dst)[32]) {
   const uint32_t a = smem_u32(src);
 #pragma unroll
