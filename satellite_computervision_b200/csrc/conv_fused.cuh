@@ -27,7 +27,16 @@
 
 namespace scv {
 
-constexpr int kF2Issuers1 = 2, kF2Issuers2 = 2;                   // issuer warps per conv (taking turns: a single issuer
+#ifndef SCV_F2_NI1
+#define SCV_F2_NI1 2
+#endif
+#ifndef SCV_F2_NS16
+#define SCV_F2_NS16 3
+#endif
+#ifndef SCV_F2_NR16
+#define SCV_F2_NR16 4
+#endif
+constexpr int kF2Issuers1 = SCV_F2_NI1, kF2Issuers2 = 2;                   // issuer warps per conv (taking turns: a single issuer
                                                                   // spends > 1000 cycles per row on waits and commits)
 // Epilogue warpgroups (four per kernel, 768 threads).  The decoder tail (fused head) gives three to conv 1 -- whose
 // proxy fence + arrive is what conv 2 waits for -- and one to the light head epilogue (13.5 ms with 2 + 2 -> 13.3 with
@@ -51,18 +60,20 @@ constexpr int kF2FirstEpi1 = 8;                                   // warps 5..7 
 __host__ __device__ constexpr int f2_threads(int epi2) { return 32 * (kF2FirstEpi1 + 4 * f2_groups(epi2)); }
 constexpr int kF2R = 8;                                           // row accumulators per conv: 8 x 32 columns = 256
 constexpr int kF2RP = kF2R / 2;
-constexpr int kF2InSlabs = 3;                                     // conv-1 input slabs (two rows of 130 px x 64 ch)
-constexpr int kF2Ring = 4;                                        // conv-1 -> conv-2 slabs (two rows of 130 px x 32 ch)
+// conv-1 input slabs (two rows of 130 px x KC1 channels) and conv-1 -> conv-2 slabs (two rows of 130 px x 32 channels);
+// the 64-channel decoder tail fills shared memory with 3 + 4, the 16-channel encoder pair has room for more
+__host__ __device__ constexpr int f2_in_slabs(int kc1) { return kc1 == 16 ? SCV_F2_NS16 : 3; }
+__host__ __device__ constexpr int f2_ring(int kc1) { return kc1 == 16 ? SCV_F2_NR16 : 4; }
 constexpr int kF2Cluster = 3;                                     // strips per image row
 static_assert(kF2FirstEpi1 % 4 == 0, "epilogue warps must start on a TMEM quadrant boundary");
 static_assert(kF2RP >= 4 && kF2RP >= kF2Issuers1 && kF2RP >= kF2Issuers2, "accumulator reuse distance (<= 4 groups per conv)");
-static_assert(kF2Issuer2Warp + kF2Issuers2 <= kF2FirstEpi1 && kF2Ring >= kF2Issuers2, "warp layout / ring depth");
+static_assert(kF2Issuer2Warp + kF2Issuers2 <= kF2FirstEpi1 && kF2Issuers1 <= 3, "warp layout / ring depth");
 
 __host__ __device__ inline size_t fused_smem_bytes(int KC1, int epi2, int ncls) {
   size_t s = 1024 + static_cast<size_t>(9) * 32 * KC1 * 2 + static_cast<size_t>(9) * 32 * 64 +
-             static_cast<size_t>(kF2InSlabs) * rows_slab_stride(KC1) + static_cast<size_t>(kF2Ring) * rows_slab_stride(32) +
+             static_cast<size_t>(f2_in_slabs(KC1)) * rows_slab_stride(KC1) + static_cast<size_t>(f2_ring(KC1)) * rows_slab_stride(32) +
              static_cast<size_t>(4 * f2_groups2(epi2)) * rows_stage_warp_bytes(epi2);
-  s += (1 + 2 * kF2InSlabs + 4 * kF2RP + kF2Issuers1 + kF2Issuers2 + 2 * kF2Ring) * 8 + 16;
+  s += (1 + 2 * f2_in_slabs(KC1) + 4 * kF2RP + kF2Issuers1 + kF2Issuers2 + 2 * f2_ring(KC1)) * 8 + 16;
   s += (32 + 32 + (epi2 == EPI_HEAD ? 32 * ncls + ncls : 64)) * 4;
   return s + 64;
 }
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
   constexpr int ROWB2 = 64, WT2 = COUT * ROWB2;             // conv-2: 32 input channels
   constexpr int ROW1 = kRowsSlabPx * ROWB1, SLAB1 = 2 * ROW1, STRIDE1 = rows_slab_stride(KC1);
   constexpr int ROW2 = kRowsSlabPx * ROWB2, STRIDE2 = rows_slab_stride(32);
-  constexpr int NS1 = kF2InSlabs, NR = kF2Ring, R = kF2R, RP = kF2RP, NI1 = kF2Issuers1, NI2 = kF2Issuers2;
+  constexpr int NS1 = f2_in_slabs(KC1), NR = f2_ring(KC1), R = kF2R, RP = kF2RP, NI1 = kF2Issuers1, NI2 = kF2Issuers2;
   constexpr uint32_t ACC2 = R * COUT;                       // first TMEM column of conv 2's accumulators
 
   extern __shared__ uint8_t smem_raw[];
