@@ -21,7 +21,11 @@
 // Ring protocol (slot s, use k): conv-1 epilogue threads wait slot_free[s], which counts one arrival per CTA whose
 // conv-2 UMMAs read a copy of the data written for use k-1 -- this CTA and its neighbour(s): each conv-2 issuer
 // multicasts ONE tcgen05.commit to the barrier at that offset in all of them.  ring_full[s] counts 128 own arrivals +
-// one per halo pixel column (remote arrive from the neighbour, or the edge thread itself at the image border) = 130.
+// one per halo pixel column = 130.  The halo pixel of a side with a neighbour arrives as an async-proxy bulk copy
+// (cp.async.bulk shared::cta -> shared::cluster, 2 rows x 64 B, complete_tx on THIS CTA's ring_full[s]); the edge thread
+// of that side contributes the matching arrive.expect_tx.  (The first version used st.shared::cluster + fence.proxy.async
+// + mbarrier.arrive.release.cluster: SASS shows a MEMBAR.ALL.GPU for each of the two -- 1 400-2 400 cycles per row pair on
+// the path conv 2 waits for.  -DSCV_F2_HALO_GENERIC keeps that version for comparison.)
 #pragma once
 #include "conv_rows.cuh"
 
@@ -96,6 +100,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// async-proxy copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer CTA's, completing on the PEER's
+// mbarrier (complete_tx): the whole transfer stays in the async proxy, no generic-proxy remote store / cluster fence
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t peer_dst, uint32_t src, uint32_t bytes, uint32_t peer_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(peer_dst),
+               "r"(src), "r"(bytes), "r"(peer_bar)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -385,7 +396,11 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
         }
         const RowsPiece pc0 = rows_piece_r<COUT, R>(tmem_base + ACC2, 2 * w, sg.npairs, opc);
         const RowsPiece pc1 = rows_piece_r<COUT, R>(tmem_base + ACC2, 2 * w + 1, sg.npairs, opc);
+#ifdef SCV_F2_HALO_GENERIC
         const bool ok2 = mbar_wait_cluster(&ring_full[rs], rph, abort_flag, p.watchdog_ns);
+#else
+        const bool ok2 = mbar_wait(&ring_full[rs], rph, abort_flag, p.watchdog_ns);
+#endif
         if (!__all_sync(0xffffffffu, ok2)) {
           run = false;
           break;
@@ -494,6 +509,7 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
           put_px(slab, px_off, pk0, false);
           put_px(slab, ROW2 + px_off, pk1, false);
           const uint32_t zero4[4] = {0u, 0u, 0u, 0u};
+#ifdef SCV_F2_HALO_GENERIC
           if (edge_l) {  // strip pixel 0: the left neighbour's halo pixel 129, or this CTA's own (zero) halo pixel 0
             if (xs > 0) {
               put_px(nb_l, (kRowsSlabPx - 1) * ROWB2, pk0, true);
@@ -512,11 +528,20 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
               put_px(slab, ROW2 + (kRowsSlabPx - 1) * ROWB2, zero4, false);
             }
           }
+#else
+          if (edge_l && xs == 0) {  // image border: this CTA's own halo pixel 0 is zero padding
+            put_px(slab, 0, zero4, false);
+            put_px(slab, ROW2, zero4, false);
+          }
+          if (edge_r && xs + 1 == kF2Cluster) {
+            put_px(slab, (kRowsSlabPx - 1) * ROWB2, zero4, false);
+            put_px(slab, ROW2 + (kRowsSlabPx - 1) * ROWB2, zero4, false);
+          }
+#endif
         }
         const long long c4 = ROWS_CLOCK();
-        // generic-proxy stores (local and remote) -> visible to the UMMAs that read the slab.  (A CTA-scoped fence for
-        // the 126 threads without remote stores measured the same: the fence waits for the shared stores, which compete
-        // with the UMMA operand fetch.)
+#ifdef SCV_F2_HALO_GENERIC
+        // generic-proxy stores (local and remote) -> visible to the UMMAs that read the slab
         fence_proxy_async_all();
         mbar_arrive(&ring_full[rs]);
         if (edge_l) {
@@ -527,6 +552,35 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
           if (xs + 1 < kF2Cluster) mbar_arrive_remote(mapa_shared(smem_u32(&ring_full[rs]), xs + 1));
           else mbar_arrive(&ring_full[rs]);
         }
+#else
+        // own generic-proxy stores -> visible to the async proxy (the UMMAs that read the slab, and the bulk copies below)
+        fence_proxy_async();
+        mbar_arrive(&ring_full[rs]);
+        // Halo exchange.  Strip pixel 0 (slab pixel 1) is the left neighbour's halo pixel 129, strip pixel 127 (slab
+        // pixel 128) the right neighbour's halo pixel 0.  Source and destination pixel are 128 pixels = 8 KB apart, so
+        // they share the SWIZZLE_64B phase and each 64-byte pixel row copies verbatim.  The copies complete_tx on the
+        // NEIGHBOUR's ring_full[rs]; the bytes flowing INTO this CTA's halo are expected by this side's edge thread.
+        if (edge_l) {
+          if (xs > 0) {
+            const uint32_t bar_l = mapa_shared(smem_u32(&ring_full[rs]), xs - 1);
+            bulk_copy_to_peer(nb_l + (kRowsSlabPx - 1) * ROWB2, slab + ROWB2, ROWB2, bar_l);
+            bulk_copy_to_peer(nb_l + ROW2 + (kRowsSlabPx - 1) * ROWB2, slab + ROW2 + ROWB2, ROWB2, bar_l);
+            mbar_arrive_expect_tx(&ring_full[rs], 2 * ROWB2);
+          } else {
+            mbar_arrive(&ring_full[rs]);
+          }
+        }
+        if (edge_r) {
+          if (xs + 1 < kF2Cluster) {
+            const uint32_t bar_r = mapa_shared(smem_u32(&ring_full[rs]), xs + 1);
+            bulk_copy_to_peer(nb_r, slab + (kRowsSlabPx - 2) * ROWB2, ROWB2, bar_r);
+            bulk_copy_to_peer(nb_r + ROW2, slab + ROW2 + (kRowsSlabPx - 2) * ROWB2, ROWB2, bar_r);
+            mbar_arrive_expect_tx(&ring_full[rs], 2 * ROWB2);
+          } else {
+            mbar_arrive(&ring_full[rs]);
+          }
+        }
+#endif
         ta_fence += ROWS_CLOCK() - c4;
         ta_math += c4 - c2;
       }
