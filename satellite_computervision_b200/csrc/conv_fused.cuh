@@ -35,10 +35,10 @@ namespace scv {
 #define SCV_F2_NI1 2
 #endif
 #ifndef SCV_F2_NS16
-#define SCV_F2_NS16 3
+#define SCV_F2_NS16 6
 #endif
 #ifndef SCV_F2_NR16
-#define SCV_F2_NR16 4
+#define SCV_F2_NR16 5
 #endif
 constexpr int kF2Issuers1 = SCV_F2_NI1, kF2Issuers2 = 2;                   // issuer warps per conv (taking turns: a single issuer
                                                                   // spends > 1000 cycles per row on waits and commits)
@@ -56,6 +56,11 @@ constexpr int kF2Issuers1 = SCV_F2_NI1, kF2Issuers2 = 2;                   // is
 #ifndef SCV_F2_GROUPS_POOL
 #define SCV_F2_GROUPS_POOL 4
 #endif
+// staging tiles per epilogue-B warp (EPI_POOL_SKIP): with 2 a warp fills one tile while the TMA stores of the previous
+// pair still read the other (cp.async.bulk.wait_group.read 1)
+#ifndef SCV_F2_NSTAGE
+#define SCV_F2_NSTAGE 1
+#endif
 __host__ __device__ constexpr int f2_groups(int epi2) { return epi2 == EPI_POOL_SKIP ? SCV_F2_GROUPS_POOL : 4; }
 __host__ __device__ constexpr int f2_groups1(int epi2) { return epi2 == EPI_POOL_SKIP ? SCV_F2_G1_POOL : SCV_F2_G1_HEAD; }
 __host__ __device__ constexpr int f2_groups2(int epi2) { return f2_groups(epi2) - f2_groups1(epi2); }
@@ -69,6 +74,7 @@ constexpr int kF2RP = kF2R / 2;
 __host__ __device__ constexpr int f2_in_slabs(int kc1) { return kc1 == 16 ? SCV_F2_NS16 : 3; }
 __host__ __device__ constexpr int f2_ring(int kc1) { return kc1 == 16 ? SCV_F2_NR16 : 4; }
 constexpr int kF2Cluster = 3;                                     // strips per image row
+static_assert(SCV_F2_NSTAGE == 1 || SCV_F2_NSTAGE == 2, "one or two staging tiles per epilogue-B warp");
 static_assert(kF2FirstEpi1 % 4 == 0, "epilogue warps must start on a TMEM quadrant boundary");
 static_assert(kF2RP >= 4 && kF2RP >= kF2Issuers1 && kF2RP >= kF2Issuers2, "accumulator reuse distance (<= 4 groups per conv)");
 static_assert(kF2Issuer2Warp + kF2Issuers2 <= kF2FirstEpi1 && kF2Issuers1 <= 3, "warp layout / ring depth");
@@ -76,7 +82,7 @@ static_assert(kF2Issuer2Warp + kF2Issuers2 <= kF2FirstEpi1 && kF2Issuers1 <= 3, 
 __host__ __device__ inline size_t fused_smem_bytes(int KC1, int epi2, int ncls) {
   size_t s = 1024 + static_cast<size_t>(9) * 32 * KC1 * 2 + static_cast<size_t>(9) * 32 * 64 +
              static_cast<size_t>(f2_in_slabs(KC1)) * rows_slab_stride(KC1) + static_cast<size_t>(f2_ring(KC1)) * rows_slab_stride(32) +
-             static_cast<size_t>(4 * f2_groups2(epi2)) * rows_stage_warp_bytes(epi2);
+             static_cast<size_t>(4 * f2_groups2(epi2)) * SCV_F2_NSTAGE * rows_stage_warp_bytes(epi2);
   s += (1 + 2 * f2_in_slabs(KC1) + 4 * kF2RP + kF2Issuers1 + kF2Issuers2 + 2 * f2_ring(KC1)) * 8 + 16;
   s += (32 + 32 + (epi2 == EPI_HEAD ? 32 * ncls + ncls : 64)) * 4;
   return s + 64;
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
   uint8_t* w1 = slabs + static_cast<size_t>(NS1) * STRIDE1;  // [kx][ky = 2,1,0][32 rows][KC1]
   uint8_t* w2 = w1 + 9 * WT1;
   uint8_t* staging = w2 + 9 * WT2;  // epilogue B's TMA-store staging tiles (EPI_POOL_SKIP)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * NG2 * STAGE_W);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * NG2 * SCV_F2_NSTAGE * STAGE_W);
   uint64_t* w_full = bars;
   uint64_t* in_full = bars + 1;
   uint64_t* in_empty = in_full + NS1;
@@ -596,13 +602,14 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
     const int g = ew >> 2;
     const int q = warp & 3;
     const uint32_t tq = tmem_base + ACC2 + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* stage = staging + static_cast<size_t>(ew) * STAGE_W;
+    uint8_t* stage_base = staging + static_cast<size_t>(ew) * (SCV_F2_NSTAGE * STAGE_W);
+    uint32_t stage_i = 0;
     const uint32_t phase = (lane >> 1) & 3;  // SWIZZLE_64B phase of staging rows `lane` and `32 + lane`
     uint32_t opc = 0;
     long long pc = p0;
     RowSeg sg;
     bool run = true;
-    long long tb_wait = 0, tb_begin = ROWS_CLOCK();
+    long long tb_wait = 0, tb_rd = 0, tb_math = 0, tb_store = 0, tb_begin = ROWS_CLOCK();
     uint32_t tb_n = 0;
     while (run && rows_next_seg(pc, p1, 1, H2, sg)) {
       for (int u = 0; u < sg.npairs; ++u) {
@@ -631,8 +638,13 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
           mbar_arrive(&acc2_empty[slot]);
         } else {
           // the row kernel's pooling epilogue (conv_rows.cuh), 16 channels at a time
-          if (lane == 0) bulk_wait_read<0>();  // the previous stores have finished reading the staging tiles
+          const long long d0 = ROWS_CLOCK();
+          uint8_t* stage = stage_base + stage_i * STAGE_W;
+          if (SCV_F2_NSTAGE > 1) stage_i ^= 1u;
+          if (lane == 0) bulk_wait_read<SCV_F2_NSTAGE - 1>();  // the stores that last read THIS tile have finished reading it
           __syncwarp();
+          const long long d1 = ROWS_CLOCK();
+          tb_rd += d1 - d0;
           const uint32_t row0 = smem_u32(stage) + lane * 64;
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {  // 8 channels = one 16-byte chunk of every staging row per step
@@ -671,6 +683,7 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
             sts128(row0 + ((static_cast<uint32_t>(c8) ^ phase) << 4), pk0[0], pk0[1], pk0[2], pk0[3]);
             sts128(row0 + 32 * 64 + ((static_cast<uint32_t>(c8) ^ phase) << 4), pk1[0], pk1[1], pk1[2], pk1[3]);
           }
+          const long long d2 = ROWS_CLOCK();
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -678,6 +691,8 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
             tma_store_4d(&tmPool, stage + 2 * 32 * 64, 0, xw >> 1, y >> 1, sg.n);
             bulk_commit();
           }
+          tb_math += d2 - d1;
+          tb_store += ROWS_CLOCK() - d2;
         }
       }
       opc += sg.npairs;
@@ -687,8 +702,8 @@ __global__ void __launch_bounds__(f2_threads(EPI2), 1)
     }
 #ifdef SCV_ROWS_PROF
     if ((p.dbg & 32) && blockIdx.x < 3 && lane == 0 && q == 0)
-      printf("[fused prof] cta %d epilogue B group %d: total %lld cyc over %u pairs: wait acc2_full %lld\n", blockIdx.x, g,
-             ROWS_CLOCK() - tb_begin, tb_n, tb_wait);
+      printf("[fused prof] cta %d epilogue B group %d: total %lld cyc over %u pairs: wait acc2_full %lld, wait staging read %lld, ld+math+sts %lld, fence+store issue %lld\n",
+             blockIdx.x, g, ROWS_CLOCK() - tb_begin, tb_n, tb_wait, tb_rd, tb_math, tb_store);
 #endif
   }
 
