@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libscv.so')
-SOURCES = ['conv_umma.cu', 'conv_rows.cu', 'conv_slabw.cu', 'conv_fused.cu', 'tile_kernels.cu', 'engine.cu']
+SOURCES = ['conv_umma.cu', 'conv_rows.cu', 'conv_slabw.cu', 'conv_slab2.cu', 'conv_fused.cu', 'tile_kernels.cu', 'engine.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

@@ -1,4 +1,5 @@
 // Instantiations + dispatch of the UMMA implicit-GEMM convolution kernels.
+#include "conv_slab2.cuh"
 #include "conv_slabw.cuh"
 #include "conv_umma.cuh"
 
@@ -132,6 +133,7 @@ cudaError_t conv_launch(const ConvLaunch& L, cudaStream_t stream) {
   if (L.slab == 5) return conv_fused_launch(L, stream);
   if (L.slab == 2) return conv_rows_launch(L, stream);
   if (L.slab == 4) return conv_slabw_launch(L, stream);
+  if (L.slab == 6) return conv_slab2_launch(L, stream);
   if (L.KC == 8) {
     switch (L.BN) {
       case 32: return launch_kc8<32>(L, stream);
@@ -164,6 +166,7 @@ cudaError_t conv_init_attributes() {
   if ((e = conv_rows_init_attributes()) != cudaSuccess) return e;
   if ((e = conv_slabw_init_attributes()) != cudaSuccess) return e;
   if ((e = conv_fused_init_attributes()) != cudaSuccess) return e;
+  if ((e = conv_slab2_init_attributes()) != cudaSuccess) return e;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }

@@ -1069,7 +1069,7 @@ struct ConvLaunch {
   CUtensorMap tmOut, tmPool;  // slab kernel only: TMA-store maps of the bf16 outputs
   ConvParams p;
   int KC, BN, EPI;
-  int slab;  // 5: conv_fused2_kernel (conv_fused.cuh; the next layer's launch is then -1 = folded into this one), 4: conv_slabw_kernel (conv_slabw.cuh), 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
+  int slab;  // 6: conv_slab2_kernel (conv_slab2.cuh, CTA pairs), 5: conv_fused2_kernel (conv_fused.cuh; the next layer's launch is then -1 = folded into this one), 4: conv_slabw_kernel (conv_slabw.cuh), 3: conv_ptile_kernel (persistent tiles), 2: conv_rows_kernel (conv_rows.cuh), 1: conv_slab_kernel, 0: conv_umma_kernel
   int nacc;  // slab kernel: accumulators / epilogue warpgroups (2 or 4)
   int grid;
   size_t smem;

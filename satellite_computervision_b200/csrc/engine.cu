@@ -20,6 +20,7 @@
 #include "../../include/scv.h"
 #include "conv_rows.cuh"
 #include "conv_fused.cuh"
+#include "conv_slab2.cuh"
 #include "conv_slabw.cuh"
 #include "conv_umma.cuh"
 #include "tile_kernels.cuh"
@@ -699,6 +700,44 @@ static bool plan_slab(const LayerDef& l, int B, int h, int w, int* bn_out, int* 
   return false;
 }
 
+// CTA-pair slab kernel (conv_slab2.cuh, tcgen05.mma.cta_group::2): the Cout = 64 3x3 layers that would run in the slab
+// kernel with N = 64 (the 192 x 192 level).  Same (chunk, tap, k) summation order -> same bits as the other 8x16-tile
+// kernels.  Measured per layer (full scene, tools/r02_exp31.sh): decoder_1/conv0 (Cin 128) 11.4 -> 7.8 ms -- the weights
+// resident per SM halve, so the slab ring covers two tiles and there are four accumulators instead of two --,
+// decoder_1/conv1 4.4 -> 3.95 ms; the K-short encoder_1/conv0 (KC 32) 2.5 -> 3.3 ms and the pooling encoder_1/conv1
+// 4.8 -> 5.9 ms are SLOWER (the pair's tile turn-around is the slower of two epilogues plus a remote arrive), so by
+// default only KC = 64 layers with the plain store epilogue take it.  SCV_SLAB2=0: off; =2: every eligible layer, any
+// launch size (tests); =3: every eligible layer at the default size threshold (experiments).
+static bool plan_slab2(const LayerDef& l, int B, int h, int w, int* nslab, int* nacc_out, int* pairs_out) {
+  const int mode = env_int("SCV_SLAB2", 1);
+  if (!mode) return false;
+  if (l.kind != L_CONV3 || l.ntotal != kSlab2BN || l.cout != kSlab2BN) return false;
+  if (l.KC != 32 && l.KC != 64) return false;
+  if (l.epi != EPI_STORE && l.epi != EPI_POOL_SKIP) return false;
+  if (mode == 1 && (l.KC != 64 || l.epi != EPI_STORE)) return false;
+  if (w % 8 || h % 16) return false;
+  const long long m_tiles = (long long)B * (h / 16) * (w / 8);
+  if (m_tiles & 1) return false;
+  if (mode != 2 && m_tiles < 8LL * sm_count()) return false;
+  const int chunks = l.cin_pad / l.KC;
+  const int slab_stride = slab_stride_bytes(l.KC, 9);
+  for (int nacc : {4, 2}) {
+    const size_t fixed = slab2_weight_bytes(l.cin_pad) + slab_stage_bytes(l.epi, nacc) + 6 * 1024;
+    const int need = std::max(2, chunks);
+    if (fixed + (size_t)need * slab_stride > kSlabSmemBudget) continue;
+    int ns = std::min(8, (int)((kSlabSmemBudget - fixed) / slab_stride));
+    if (const int o = env_int("SCV_SLAB_STAGES", 0)) ns = std::max(need, std::min(ns, o));
+    if (ns >= 2 * chunks) ns = ns / (2 * chunks) * (2 * chunks);  // two issuers: see conv_slab_kernel
+    const int pairs = conv_slab2_max_pairs(slab2_smem_bytes(l.KC, l.cin_pad, ns, l.epi, nacc), nacc);
+    if (pairs < 8) return false;  // cluster launch not available
+    *nslab = ns;
+    *nacc_out = nacc;
+    *pairs_out = pairs;
+    return true;
+  }
+  return false;
+}
+
 // Row-streaming tap-packed kernel (conv_rows.cuh): 3x3 layers with Cout 32/64 on rows that split into
 // 128-pixel strips.  The choice depends on the layer geometry only -- never on the batch size -- so a
 // tile's result does not depend on how many tiles ran with it.
@@ -797,6 +836,25 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     L->smem = slabw_smem_bytes(64, wn, nbr, l.epi);
     if (l.BN != wn) SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, wn));
     else L->tmB = l.tmB;
+    SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, 10, 18, 1));
+    return SCV_OK;
+  }
+  int pairs = 0;
+  if (plan_slab2(l, B, h, w, &ns, &nacc, &pairs)) {
+    L->nacc = nacc;
+    L->slab = 6;
+    L->BN = kSlab2BN;
+    p.TW = 8, p.TH = 16, p.TN = 1;
+    p.tiles_x = w / 8;
+    p.tiles_y = h / 16;
+    p.tiles_n = B;
+    p.num_m_tiles = p.tiles_x * p.tiles_y * B;
+    p.n_tiles_n = 1;
+    p.nslab = ns;
+    p.n_issuers = (ns % (2 * (l.cin_pad / l.KC)) == 0) ? 2 : 1;
+    L->grid = 2 * (int)std::min<long long>({(long long)pairs, (long long)sm_count() / 2, (long long)p.num_m_tiles / 2});
+    L->smem = slab2_smem_bytes(l.KC, l.cin_pad, ns, l.epi, nacc);
+    SCV_TRY(make_w_tmap(&L->tmB, l.d_w, (int)k_total(l.KC, 9, l.cin_pad), l.ntotal, l.KC, kSlab2BH));
     SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, 10, 18, 1));
     return SCV_OK;
   }
@@ -934,8 +992,8 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
     SCV_TRY(finish_slab_maps(&Ln, l));
     if (env_int("SCV_PLAN_DEBUG", 0))
       fprintf(stderr, "[scv plan B=%d] %-18s %dx%d Cin=%d N=%d  %s KC=%d BN=%d %s=%d nacc=%d grid=%d smem=%zu\n", B,
-              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 4 ? "slabw" : (Ln.slab == 3 ? "ptile" : (Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile"))), Ln.KC, Ln.BN,
-              (Ln.slab == 1 || Ln.slab == 2) ? "nslab" : "nstage", (Ln.slab == 1 || Ln.slab == 2) ? Ln.p.nslab : Ln.p.nstage,
+              l.name.c_str(), h, w, l.cin_pad, l.ntotal, Ln.slab == 6 ? "slab2" : Ln.slab == 4 ? "slabw" : (Ln.slab == 3 ? "ptile" : (Ln.slab == 2 ? "rows" : (Ln.slab ? "slab" : "tile"))), Ln.KC, Ln.BN,
+              (Ln.slab == 1 || Ln.slab == 2 || Ln.slab == 6) ? "nslab" : "nstage", (Ln.slab == 1 || Ln.slab == 2 || Ln.slab == 6) ? Ln.p.nslab : Ln.p.nstage,
               Ln.slab == 3 ? 2 : (Ln.slab ? Ln.nacc : 1), Ln.grid, Ln.smem);
     pl->launches.push_back(Ln);
   }
@@ -2174,7 +2232,10 @@ static int debug_conv(int device, int kind, const float* x, int N, int H, int W,
       Ln.smem = conv_smem_bytes(l.KC, l.BN, Ln.p.nstage, l.epi, 1);
     }
   if (const char* s = getenv("SCV_DEBUG_GRID"))  // persistent kernels: fewer CTAs -> longer streams per CTA
-    if (Ln.slab && atoi(s) > 0) Ln.grid = std::max(Ln.p.n_tiles_n, std::min(Ln.grid, atoi(s)) / Ln.p.n_tiles_n * Ln.p.n_tiles_n);
+    if (Ln.slab && atoi(s) > 0) {
+      Ln.grid = std::max(Ln.p.n_tiles_n, std::min(Ln.grid, atoi(s)) / Ln.p.n_tiles_n * Ln.p.n_tiles_n);
+      if (Ln.slab == 6) Ln.grid = std::max(2, Ln.grid & ~1);
+    }
   Ln.p.relu = relu;
   Ln.p.out = d_y;
   Ln.p.out_pitch = Cout;

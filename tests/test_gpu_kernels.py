@@ -179,6 +179,35 @@ def test_weight_streaming_slab_kernel(N, H, W, Cin, Cout, grid, monkeypatch):
     assert np.array_equal(y, ref_kernel) and np.array_equal(p, G.maxpool_ref(y))
 
 
+@pytest.mark.parametrize('N,H,W,Cin,Cout,grid', [
+    (2, 32, 32, 64, 64, 0),       # one chunk, 16 tiles = 8 pairs, single pass
+    (1, 48, 96, 128, 64, 4),      # two chunks (decoder_1/conv0 shape), 36 tiles over 2 pairs: 9 rounds, rings wrap
+    (3, 32, 16, 32, 64, 2),       # KC = 32 (encoder_1/conv0 shape), 12 tiles over one pair, two issuers alternate
+    (2, 16, 48, 64, 64, 6),       # 12 tiles over 3 pairs
+    (1, 64, 64, 192, 64, 2),      # three chunks: three slabs, single issuer, one pair
+])
+def test_cta_pair_slab_kernel(N, H, W, Cin, Cout, grid, monkeypatch):
+    """conv_slab2_kernel (tcgen05.mma.cta_group::2: M = 256 over a CTA pair, each CTA holds half of the weights)
+    against torch and, bit for bit, against the one-tile-per-CTA kernel (same (chunk, tap, k) summation order);
+    pooled + skip epilogue too."""
+    rng = np.random.default_rng(77 + N + H + Cin)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    k = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) * 0.1
+    for name in ('SCV_ROWS', 'SCV_SLAB', 'SCV_PTILE', 'SCV_SLABW', 'SCV_SLAB2'):
+        monkeypatch.setenv(name, '0')
+    ref_kernel = G.conv3x3_device(x, k, b)
+    monkeypatch.setenv('SCV_SLAB2', '2')
+    if grid:
+        monkeypatch.setenv('SCV_DEBUG_GRID', str(grid))
+    got = G.conv3x3_device(x, k, b)
+    s = G.err_stats(got, G.conv3x3_ref(x, k, b))
+    assert s['nan'] == 0 and s['n_bad'] == 0, s
+    assert np.array_equal(got, ref_kernel)
+    y, p = G.conv3x3_device(x, k, b, pooled=True)
+    assert np.array_equal(y, ref_kernel) and np.array_equal(p, G.maxpool_ref(y))
+
+
 def test_persistent_tile_kernel_convT(monkeypatch):
     rng = np.random.default_rng(41)
     x = rng.standard_normal((2, 6, 6, 1024)).astype(np.float32)

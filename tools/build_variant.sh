@@ -7,6 +7,6 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 SRC=$ROOT/satellite_computervision_b200/csrc
 OUT=$ROOT/tools/microbench/build; mkdir -p $OUT/$NAME
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $DEFS"
-for f in conv_umma conv_rows conv_slabw conv_fused tile_kernels engine; do nvcc $FLAGS -c $SRC/$f.cu -o $OUT/$NAME/$f.o & done; wait
+for f in conv_umma conv_rows conv_slabw conv_slab2 conv_fused tile_kernels engine; do nvcc $FLAGS -c $SRC/$f.cu -o $OUT/$NAME/$f.o & done; wait
 nvcc -shared -o $OUT/libscv_$NAME.so $OUT/$NAME/*.o -cudart static
 echo $OUT/libscv_$NAME.so
