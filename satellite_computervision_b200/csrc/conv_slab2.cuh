@@ -276,10 +276,11 @@ __global__ void __launch_bounds__(slab2_threads(NACC), 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
       epilogue_slab<BN, EPI>(p, &tmOut, &tmPool, taddr, lane, q, tx * 8, ty * 16, n, 0, s_bias, s_extra,
-                             staging + static_cast<size_t>(warp - kFirstEpiWarp) * slab_stage_warp_bytes(EPI));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_pair(acc_empty_L);
+                             staging + static_cast<size_t>(warp - kFirstEpiWarp) * slab_stage_warp_bytes(EPI), [&] {
+                               tc_fence_before();  // every lane's tcgen05.ld has completed (wait::ld is warp-wide)
+                               __syncwarp();
+                               if (lane == 0) mbar_arrive_pair(acc_empty_L);
+                             });
     }
     if (lane == 0) bulk_wait_read<0>();  // staging must stay valid until the last stores have read it
   }

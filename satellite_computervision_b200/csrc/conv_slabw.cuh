@@ -254,9 +254,10 @@ __global__ void __launch_bounds__(kSlabwThreads, 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + g * BN + (static_cast<uint32_t>(q * 32) << 16);
       epilogue_slab<BN, EPI>(p, &tmOut, &tmPool, taddr, lane, q, tx * 8, ty * 16, n, nb0, s_bias, s_extra,
-                             staging + static_cast<size_t>(warp - kSlabwFirstEpiWarp) * slab_stage_warp_bytes(EPI));
-      tc_fence_before();
-      mbar_arrive(&acc_empty[g]);
+                             staging + static_cast<size_t>(warp - kSlabwFirstEpiWarp) * slab_stage_warp_bytes(EPI), [&] {
+                               tc_fence_before();
+                               mbar_arrive(&acc_empty[g]);
+                             });
     }
     if (lane == 0) bulk_wait_read<0>();  // staging must stay valid until the last stores have read it
   }

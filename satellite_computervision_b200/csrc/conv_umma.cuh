@@ -256,10 +256,13 @@ __host__ __device__ constexpr int slab_stage_warp_bytes(int epi) {
   return epi == EPI_HEAD ? 0 : (kStageOutBytes + (epi == EPI_POOL_SKIP ? kStagePoolBytes : 0));
 }
 
-template <int BN, int EPI>
+// `release()` runs right after the LAST tcgen05.ld of the tile has completed: the accumulator is handed back to the
+// issuer while this warp still does the last block's math, staging and store (early release; the kernels used to
+// arrive only after the whole epilogue, i.e. also after the wait for the previous TMA store's read-out).
+template <int BN, int EPI, typename Release>
 __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmPool,
                                               uint32_t taddr, int lane, int q, int x0, int y0, int n, int nb0,
-                                              const float* s_bias, const float* s_extra, uint8_t* stage) {
+                                              const float* s_bias, const float* s_extra, uint8_t* stage, Release&& release) {
   const int xx = lane & 7, yl = lane >> 3;
   // swizzle phase of a 64-byte staging row = absolute smem address bits [7,9) (SWIZZLE_64B)
   const uint32_t phase = (lane >> 1) & 3;
@@ -278,6 +281,7 @@ __device__ __forceinline__ void epilogue_slab(const ConvParams& p, const CUtenso
     float v[32];
     lds32(s_bias + col, v);
     tmem_ld_wait();
+    if (blk == BN / 32 - 1) release();
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       v[j] += __uint_as_float(raw[j]);
@@ -1022,11 +1026,22 @@ __global__ void __launch_bounds__(slab_threads(NACC), 1)
         epilogue_head<BN>(p, taddr, xx, yy, x, y, n, (x < p.W) && (y < p.H), nb0, s_bias, s_extra);
       } else {
         epilogue_slab<BN, EPI>(p, &tmOut, &tmPool, taddr, lane, q, tx * 8, ty * 16, n, nb0, s_bias, s_extra,
-                               staging + static_cast<size_t>(warp - kFirstEpiWarp) * slab_stage_warp_bytes(EPI));
+                               staging + static_cast<size_t>(warp - kFirstEpiWarp) * slab_stage_warp_bytes(EPI), [&] {
+                                 tc_fence_before();
+                                 mbar_arrive(&acc_empty[g]);
+                               });
       }
 #endif
-      tc_fence_before();
-      mbar_arrive(&acc_empty[g]);
+      if constexpr (EPI == EPI_HEAD) {
+        tc_fence_before();
+        mbar_arrive(&acc_empty[g]);
+      }
+#if defined(SCV_DBG_NO_EPILOGUE)
+      else {
+        tc_fence_before();
+        mbar_arrive(&acc_empty[g]);
+      }
+#endif
     }
     if constexpr (EPI != EPI_HEAD) {
       if (lane == 0) bulk_wait_read<0>();  // staging must stay valid until the last stores have read it
