@@ -11,7 +11,7 @@ for line in open('/tmp/scv.sass'):
     m = re.search(r'Function : (\S+)', line)
     if m:
         name = m.group(1)
-        f = re.search(r'(conv_fused2_kernel|conv_rows_kernel|conv_slabw_kernel|conv_slab_kernel|conv_ptile_kernel|conv_umma_kernel|extract_u16x6_kernel|extract_kernel|stitch_kernel_vec|stitch_kernel_scalar|tile_stats_kernel|head_tiles_kernel)', name)
+        f = re.search(r'(conv_fused2_kernel|conv_rows_kernel|conv_slabw_kernel|conv_slab2_kernel|conv_slab_kernel|conv_ptile_kernel|conv_umma_kernel|extract_u16x6_kernel|extract_kernel|stitch_kernel_vec|stitch_kernel_scalar|tile_stats_kernel|head_tiles_kernel)', name)
         cur = f.group(1) if f else 'other'
         fam.setdefault(cur, collections.Counter())['__instances'] += 1
         continue
