@@ -49,6 +49,9 @@ typedef struct scv_engine scv_engine;
 enum { SCV_U8 = 0, SCV_U16 = 1, SCV_I16 = 2, SCV_F32 = 3, SCV_F64 = 4 };
 /* heads: utils/model_tools.py:443-445 (sigmoid, strict >thr) and :405-406 (softmax, argmax) */
 enum { SCV_HEAD_SIGMOID = 0, SCV_HEAD_SOFTMAX = 1 };
+/* network families: the U-Net of get_unet_model / binary_unet (utils/model_tools.py:394-454) and the siamese U-Net with an
+ * atrous spatial pyramid of make_siamese_unet (utils/model_tools.py:533-663) */
+enum { SCV_ARCH_UNET = 0, SCV_ARCH_SIAMESE = 1 };
 /* normaliser fused into the extract kernel */
 enum {
   SCV_NORM_NONE = 0,
@@ -92,6 +95,12 @@ typedef struct {
   int head;                    /* SCV_HEAD_*                                               */
   float threshold;             /* sigmoid class threshold (0.5; 0.9 for solar, :444)       */
   int max_batch;               /* tiles per device batch (0 = default 64)                  */
+  int arch;                    /* SCV_ARCH_*.  SCV_ARCH_SIAMESE: make_siamese_unet(n_channels, filters, factors)
+                                  (model_tools.py:638-663): `nchannels` is the band count of ONE image; every input
+                                  (tiles, patches, mosaics) carries the two images stacked along the channel axis,
+                                  [input_a | input_b] = 2 * nchannels bands; shared single-conv encoder blocks,
+                                  ASPP (1x1 + 3x3 at dilation 3 / 6 / 12 -> 1x1) on both pooled images, decoder over
+                                  concat([encoded_b, encoded_a, up]); sigmoid head, strict > threshold           */
 } scv_config;
 
 /* One Keras weight array, fp32, C-contiguous, Keras layout (Conv2D HWIO,

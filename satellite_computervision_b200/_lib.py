@@ -28,10 +28,13 @@ class ScvError(RuntimeError):
         self.code = code
 
 
+SCV_ARCH_UNET, SCV_ARCH_SIAMESE = 0, 1
+
+
 class Config(C.Structure):
     _fields_ = [('device', C.c_int), ('double_conv', C.c_int), ('nchannels', C.c_int), ('nclasses', C.c_int),
                 ('nlevels', C.c_int), ('filters', C.c_int * SCV_MAX_LEVELS), ('head', C.c_int),
-                ('threshold', C.c_float), ('max_batch', C.c_int)]
+                ('threshold', C.c_float), ('max_batch', C.c_int), ('arch', C.c_int)]
 
 
 class Tensor(C.Structure):

@@ -54,6 +54,7 @@ struct ConvParams {
   // persistent slab kernel
   int n_in_off;         // image offset added to the A-operand TMA coordinate (layer input is a slice of a larger tensor)
   int nslab;            // slab ring depth
+  int dil;              // dilation of the 3x3 taps (tile kernels only; 1 everywhere but the siamese network's ASPP)
   int n_issuers;        // MMA issuer warps in use (1 or 2); 2 requires nslab % (2 * Cin/KC) == 0
   int num_m_tiles;      // tiles_x * tiles_y * N
   int dbg;              // timing experiments only (env SCV_ROWS_DBG; results are wrong when non-zero)
@@ -501,8 +502,8 @@ __global__ void __launch_bounds__(kConvThreads)
       if (!__all_sync(0xffffffffu, ok)) break;
       int dy = 0, dx = 0;
       if (p.ntaps == 9) {
-        dy = tap / 3 - 1;
-        dx = tap % 3 - 1;
+        dy = (tap / 3 - 1) * p.dil;
+        dx = (tap % 3 - 1) * p.dil;
       }
       uint8_t* a_dst = tiles + static_cast<size_t>(s) * STAGE_BYTES;
       if (elect_one()) {
@@ -678,8 +679,8 @@ __global__ void __launch_bounds__(kPtileThreads, 1)
         }
         int dy = 0, dx = 0;
         if (p.ntaps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
+          dy = (tap / 3 - 1) * p.dil;
+          dx = (tap % 3 - 1) * p.dil;
         }
         uint8_t* a_dst = tiles + static_cast<size_t>(s) * STAGE_BYTES;
         if (elect_one()) {

@@ -180,11 +180,22 @@ static int validate_config(const scv_config* c) {
       return fail(SCV_ERR_INVALID, "filters[%d]=%d unsupported: must be 32 or a multiple of 64", i, f);
   }
   if (c->filters[0] > 128) return fail(SCV_ERR_INVALID, "filters[0]=%d > 128 unsupported by the fused head", c->filters[0]);
+  if (c->arch != SCV_ARCH_UNET && c->arch != SCV_ARCH_SIAMESE) return fail(SCV_ERR_INVALID, "unknown arch %d", c->arch);
+  if (c->arch == SCV_ARCH_SIAMESE) {
+    if (2 * c->nchannels > SCV_MAX_BANDS)
+      return fail(SCV_ERR_INVALID, "siamese: 2 x nchannels = %d exceeds %d bands", 2 * c->nchannels, SCV_MAX_BANDS);
+    if (c->double_conv) return fail(SCV_ERR_INVALID, "siamese: encoder blocks are single conv-BN-ReLU (conv_block.call as written)");
+    if (c->head != SCV_HEAD_SIGMOID) return fail(SCV_ERR_INVALID, "siamese: the head is Conv2D(1, 1x1, sigmoid) (model_tools.py:659)");
+  }
   return SCV_OK;
 }
+// bands of the input rasters / tiles: the siamese network takes its two images stacked along the channel axis
+static int input_channels(const scv_config* c) { return c->arch == SCV_ARCH_SIAMESE ? 2 * c->nchannels : c->nchannels; }
 
+static void build_specs_siamese(const scv_config* c, std::vector<WeightSpec>* out);
 // keras model.get_weights() order (see oracle/unet.py weight_specs for the same walk)
 static void build_specs(const scv_config* c, std::vector<WeightSpec>* out) {
+  if (c->arch == SCV_ARCH_SIAMESE) return build_specs_siamese(c, out);
   auto add = [&](const std::string& n, std::initializer_list<int64_t> s) {
     WeightSpec w;
     w.name = n;
@@ -235,14 +246,72 @@ static void build_specs(const scv_config* c, std::vector<WeightSpec>* out) {
   conv("head", cin, c->nclasses, 1);
 }
 
+// make_siamese_unet / get_siamese_layers / DilatedSpatialPyramidPooling (utils/model_tools.py:533-663), per conv-BN unit
+// in (kernel, bias, gamma, beta, moving_mean, moving_variance) order (oracle/siamese.py walks the same list; the Python
+// layer maps tf.keras' trainable-first order of the ASPP layer onto it).
+static void build_specs_siamese(const scv_config* c, std::vector<WeightSpec>* out) {
+  auto add = [&](const std::string& n, std::initializer_list<int64_t> s) {
+    WeightSpec w;
+    w.name = n;
+    w.ndim = (int)s.size();
+    int i = 0;
+    for (auto v : s) w.shape[i++] = v;
+    for (; i < 4; ++i) w.shape[i] = 1;
+    out->push_back(w);
+  };
+  auto conv = [&](const std::string& n, int cin, int cout, int k) {
+    add(n + "/kernel", {k, k, cin, cout});
+    add(n + "/bias", {cout});
+  };
+  auto bn = [&](const std::string& n, int ch) {
+    add(n + "/gamma", {ch});
+    add(n + "/beta", {ch});
+    add(n + "/moving_mean", {ch});
+    add(n + "/moving_variance", {ch});
+  };
+  const int L = c->nlevels;
+  int cin = c->nchannels;
+  for (int i = 0; i < L; ++i) {
+    const std::string b = "encoder_" + std::to_string(i);
+    conv(b + "/conv0", cin, c->filters[i], 3);
+    bn(b + "/bn0", c->filters[i]);
+    cin = c->filters[i];
+  }
+  const int nf = 2 * c->filters[L - 1];
+  conv("ASPP/cba/conv", cin, nf, 1);
+  bn("ASPP/cba/bn", nf);
+  conv("ASPP/cba3/conv", 4 * nf, nf, 1);
+  bn("ASPP/cba3/bn", nf);
+  for (int r : {3, 6, 12}) {
+    const std::string b = "ASPP/cba3_" + std::to_string(r);
+    conv(b + "/conv", cin, nf, 3);
+    bn(b + "/bn", nf);
+  }
+  cin = 2 * nf;
+  for (int i = L - 1; i >= 0; --i) {
+    const int f = c->filters[i];
+    const std::string b = "decoder_" + std::to_string(i);
+    add(b + "/up/kernel", {2, 2, f, cin});
+    add(b + "/up/bias", {f});
+    bn(b + "/bn_cat", 3 * f);
+    conv(b + "/conv0", 3 * f, f, 3);
+    bn(b + "/bn0", f);
+    conv(b + "/conv1", f, f, 3);
+    bn(b + "/bn1", f);
+    cin = f;
+  }
+  conv("head", cin, c->nclasses, 1);
+}
+
 // ---- layer graph -----------------------------------------------------------
-enum { L_CONV3 = 0, L_CONVT = 1 };
+enum { L_CONV3 = 0, L_CONVT = 1, L_CONV1 = 2 };
 
 struct BufDef {
   int level;     // resolution = tile >> level
   int channels;  // channel pitch
   bool f32;      // logits
   std::string name;
+  int mult = 1;  // images per tile (2: the siamese network's A half then B half)
 };
 
 struct LayerDef {
@@ -259,6 +328,13 @@ struct LayerDef {
   int w_skip_bn;               // EPI_POOL_SKIP: decoder bn_cat gamma index (first F channels)
   int w_up_bn;                 // L_CONVT: decoder bn_cat gamma index (channels [F,2F))
   double flops_per_tile_at_unit;  // FLOPs per input pixel of this layer (multiply by h*w of its level)
+  // siamese network (all zero / one for the plain U-Net)
+  int dil = 1;         // dilation rate of a 3x3 conv (ASPP: 3, 6, 12)
+  int cin_off = 0;     // first input channel the kernel applies to (the two images are stacked along the channel axis)
+  int skip_off = 0;    // EPI_POOL_SKIP: first channel of this layer's slice of the decoder's bn_cat
+  int up_off = -1;     // L_CONVT: first channel of the up slice of bn_cat (-1: cout, the plain U-Net's [F, 2F))
+  int nmult = 1;       // images per tile this launch covers (2: both halves of a mult-2 buffer as one batch)
+  int in_half = 0, out_half = 0, pool_half = 0;  // which half of a mult-2 buffer the launch reads / writes
   // device weights
   __nv_bfloat16* d_w = nullptr;
   float* d_bias = nullptr;
@@ -280,11 +356,13 @@ struct Arch {
   int c0pad;
 };
 
+static int build_arch_siamese(const scv_config* c, Arch* a);
 static int build_arch(const scv_config* c, Arch* a) {
   SCV_TRY(validate_config(c));
   a->cfg = *c;
   build_specs(c, &a->specs);
   for (size_t i = 0; i < a->specs.size(); ++i) a->spec_index[a->specs[i].name] = (int)i;
+  if (c->arch == SCV_ARCH_SIAMESE) return build_arch_siamese(c, a);
   auto idx = [&](const std::string& n) { return a->spec_index.at(n); };
   auto add_buf = [&](int level, int ch, bool f32, const std::string& n) {
     a->bufs.push_back({level, ch, f32, n});
@@ -396,6 +474,164 @@ static int build_arch(const scv_config* c, Arch* a) {
       c1.epi = EPI_HEAD;
       c1.out_buf = a->logits_buf;
       c1.flops_per_tile_at_unit += 2.0 * f * c->nclasses;  // fused 1x1 head
+    } else {
+      c1.out_buf = d2[i];
+    }
+    a->layers.push_back(c1);
+    cur = c1.out_buf;
+    cur_real = f;
+  }
+  for (auto& l : a->layers) {
+    if (l.BN == 0) return fail(SCV_ERR_INVALID, "layer %s: N=%d has no supported tile width", l.name.c_str(), l.ntotal);
+    if (l.cin_pad % l.KC != 0) return fail(SCV_ERR_INVALID, "layer %s: Cin pad %d vs KC %d", l.name.c_str(), l.cin_pad, l.KC);
+  }
+  if ((int)a->layers.size() > SCV_MAX_LAYERS) return fail(SCV_ERR_INVALID, "too many layers");
+  return SCV_OK;
+}
+
+// Siamese U-Net with an atrous pyramid between encoder and decoder: make_siamese_unet / get_siamese_layers /
+// DilatedSpatialPyramidPooling (utils/model_tools.py:533-663).  The two images arrive stacked along the channel axis
+// ([a | b], so every tiled-predict entry point works unchanged); the shared encoder runs once per image (the first
+// conv reads the stacked tile with its kernel embedded at channel offset 0 / C), every later encoder conv reads the A /
+// B half of a two-images-per-tile buffer.  Concatenations cost nothing: the encoder epilogues write relu(bn_cat(.)) of
+// their output straight into channel slices [0, F) (image b) / [F, 2F) (image a) of the decoder-entry tensor, the
+// transposed conv into [2F, 3F); the four ASPP branches write the four slices of one 4 nf-channel tensor.
+static int build_arch_siamese(const scv_config* c, Arch* a) {
+  auto idx = [&](const std::string& n) { return a->spec_index.at(n); };
+  auto add_buf = [&](int level, int ch, bool f32, const std::string& n, int mult) {
+    BufDef b{level, ch, f32, n};
+    b.mult = mult;
+    a->bufs.push_back(b);
+    return (int)a->bufs.size() - 1;
+  };
+  const int L = c->nlevels, C = c->nchannels;
+  a->c0pad = pad_channels(2 * C);
+  a->x0_buf = add_buf(0, a->c0pad, false, "x0", 1);
+  std::vector<int> cat(L), pooled(L), t(L), d2(L, -1);
+  for (int i = 0; i < L; ++i) {
+    cat[i] = add_buf(i, pad_channels(3 * c->filters[i]), false, "cat" + std::to_string(i), 1);
+    pooled[i] = add_buf(i + 1, c->filters[i], false, "pool" + std::to_string(i), 2);
+    t[i] = add_buf(i, c->filters[i], false, "t" + std::to_string(i), 1);
+    if (i > 0) d2[i] = add_buf(i, c->filters[i], false, "dec" + std::to_string(i), 1);
+  }
+  const int FL = c->filters[L - 1], nf = 2 * FL;
+  const int aspp_cat = add_buf(L, 4 * nf, false, "aspp_cat", 2);
+  const int squeezed = add_buf(L, 2 * nf, false, "squeezed", 1);
+  a->logits_buf = add_buf(0, c->nclasses, true, "logits", 1);
+
+  auto conv_layer = [&](const std::string& wname, const std::string& name, int kind, int level, int cin_real, int in_buf,
+                        int cout) {
+    LayerDef l{};
+    l.name = name;
+    l.kind = kind;
+    l.epi = EPI_STORE;
+    l.level = level;
+    l.cin_real = cin_real;
+    l.cin_pad = a->bufs[in_buf].channels;
+    l.cout = cout;
+    l.ntotal = cout;
+    l.KC = kc_for(l.cin_pad);
+    l.BN = bn_for(cout);
+    l.in_buf = in_buf;
+    l.out_buf = -1;
+    l.out_choff = 0;
+    l.pool_buf = -1;
+    l.w_kernel = idx(wname + "/kernel");
+    l.w_bias = idx(wname + "/bias");
+    l.w_bn = -1;
+    l.w_skip_bn = l.w_up_bn = -1;
+    l.flops_per_tile_at_unit = 2.0 * cin_real * cout * (kind == L_CONV3 ? 9 : 1);
+    return l;
+  };
+
+  // shared encoder: image a (first C channels) then image b; net[i] = concat([encoded_b, encoded_a]) (:604, :609)
+  for (int i = 0; i < L; ++i) {
+    const std::string b = "encoder_" + std::to_string(i);
+    const int F = c->filters[i];
+    for (int half = 0; half < 2; ++half) {
+      LayerDef l = conv_layer(b + "/conv0", b + (half ? "/conv0[b]" : "/conv0[a]"), L_CONV3, i, i == 0 ? C : c->filters[i - 1],
+                              i == 0 ? a->x0_buf : pooled[i - 1], F);
+      l.w_bn = idx(b + "/bn0/gamma");
+      l.epi = EPI_POOL_SKIP;
+      l.out_buf = cat[i];
+      l.out_choff = half ? 0 : F;
+      l.skip_off = l.out_choff;
+      l.w_skip_bn = idx("decoder_" + std::to_string(i) + "/bn_cat/gamma");
+      l.pool_buf = pooled[i];
+      l.pool_half = half;
+      if (i == 0) l.cin_off = half ? C : 0;
+      else l.in_half = half;
+      a->layers.push_back(l);
+    }
+  }
+  // ASPP on both pooled images as one batch (:561-573): 1x1 and three dilated 3x3 branches -> concat -> 1x1
+  {
+    LayerDef l = conv_layer("ASPP/cba/conv", "ASPP/cba", L_CONV1, L, FL, pooled[L - 1], nf);
+    l.w_bn = idx("ASPP/cba/bn/gamma");
+    l.out_buf = aspp_cat;
+    l.nmult = 2;
+    l.flops_per_tile_at_unit *= 2;
+    a->layers.push_back(l);
+    int k = 1;
+    for (int r : {3, 6, 12}) {
+      const std::string n = "ASPP/cba3_" + std::to_string(r);
+      LayerDef d = conv_layer(n + "/conv", n, L_CONV3, L, FL, pooled[L - 1], nf);
+      d.w_bn = idx(n + "/bn/gamma");
+      d.dil = r;
+      d.out_buf = aspp_cat;
+      d.out_choff = k++ * nf;
+      d.nmult = 2;
+      d.flops_per_tile_at_unit *= 2;
+      a->layers.push_back(d);
+    }
+    for (int half = 0; half < 2; ++half) {  // squeezed = concat([aspp_b, aspp_a]) (:620)
+      LayerDef o = conv_layer("ASPP/cba3/conv", half ? "ASPP/cba3[b]" : "ASPP/cba3[a]", L_CONV1, L, 4 * nf, aspp_cat, nf);
+      o.w_bn = idx("ASPP/cba3/bn/gamma");
+      o.in_half = half;
+      o.out_buf = squeezed;
+      o.out_choff = half ? 0 : nf;
+      a->layers.push_back(o);
+    }
+  }
+  int cur = squeezed, cur_real = 2 * nf;
+  for (int i = L - 1; i >= 0; --i) {
+    const int f = c->filters[i];
+    const std::string b = "decoder_" + std::to_string(i);
+    LayerDef u{};
+    u.name = b + "/up";
+    u.kind = L_CONVT;
+    u.epi = EPI_CONVT;
+    u.level = i + 1;
+    u.cin_real = cur_real;
+    u.cin_pad = a->bufs[cur].channels;
+    u.cout = f;
+    u.ntotal = 4 * f;
+    u.KC = kc_for(u.cin_pad);
+    u.BN = bn_for(u.ntotal);
+    u.in_buf = cur;
+    u.out_buf = cat[i];
+    u.out_choff = 2 * f;
+    u.up_off = 2 * f;
+    u.pool_buf = -1;
+    u.w_kernel = idx(b + "/up/kernel");
+    u.w_bias = idx(b + "/up/bias");
+    u.w_bn = -1;
+    u.w_skip_bn = -1;
+    u.w_up_bn = idx(b + "/bn_cat/gamma");
+    u.flops_per_tile_at_unit = 2.0 * cur_real * f * 4;
+    a->layers.push_back(u);
+
+    LayerDef c0 = conv_layer(b + "/conv0", b + "/conv0", L_CONV3, i, 3 * f, cat[i], f);
+    c0.w_bn = idx(b + "/bn0/gamma");
+    c0.out_buf = t[i];
+    a->layers.push_back(c0);
+
+    LayerDef c1 = conv_layer(b + "/conv1", b + "/conv1", L_CONV3, i, f, t[i], f);
+    c1.w_bn = idx(b + "/bn1/gamma");
+    if (i == 0) {
+      c1.epi = EPI_HEAD;
+      c1.out_buf = a->logits_buf;
+      c1.flops_per_tile_at_unit += 2.0 * f * c->nclasses;
     } else {
       c1.out_buf = d2[i];
     }
@@ -584,19 +820,19 @@ static int fold_and_upload(scv_engine* e, const scv_tensor* t) {
     std::vector<float> w((size_t)l.ntotal * ktotal, 0.f), bias(l.ntotal, 0.f);
     const float* K = t[l.w_kernel].data;
     const float* Bv = t[l.w_bias].data;
-    if (l.kind == L_CONV3) {
+    if (l.kind == L_CONV3 || l.kind == L_CONV1) {
       std::vector<float> s, sh;
       bn_affine(t, l.w_bn, 0, l.cout, &s, &sh);
-      // keras HWIO (3,3,Cin,Cout) -> [o][tap*cin_pad + c] with W' = W*s[o]
-      for (int tap = 0; tap < 9; ++tap)
+      // keras HWIO (k,k,Cin,Cout) -> [o][tap*cin_pad + cin_off + c] with W' = W*s[o]
+      for (int tap = 0; tap < ntaps; ++tap)
         for (int c = 0; c < l.cin_real; ++c) {
           const float* src = K + ((size_t)tap * l.cin_real + c) * l.cout;
-          for (int o = 0; o < l.cout; ++o) w[(size_t)o * ktotal + (size_t)tap * l.cin_pad + c] = src[o] * s[o];
+          for (int o = 0; o < l.cout; ++o) w[(size_t)o * ktotal + (size_t)tap * l.cin_pad + l.cin_off + c] = src[o] * s[o];
         }
       for (int o = 0; o < l.cout; ++o) bias[o] = Bv[o] * s[o] + sh[o];  // (b - mean)*s + beta
       std::vector<float> ks, kt;
       if (l.epi == EPI_POOL_SKIP) {
-        bn_affine(t, l.w_skip_bn, 0, l.cout, &ks, &kt);
+        bn_affine(t, l.w_skip_bn, l.skip_off, l.cout, &ks, &kt);
         SCV_TRY(upload_layer(l, w, bias, &ks, &kt));
       } else {
         SCV_TRY(upload_layer(l, w, bias, nullptr, nullptr));
@@ -606,7 +842,7 @@ static int fold_and_upload(scv_engine* e, const scv_tensor* t) {
       // concat is folded on the up half: W' = W*s2[o], b' = b*s2[o] + t2[o]
       const int F = l.cout;
       std::vector<float> s2, t2;
-      bn_affine(t, l.w_up_bn, F, F, &s2, &t2);
+      bn_affine(t, l.w_up_bn, l.up_off >= 0 ? l.up_off : F, F, &s2, &t2);
       for (int ab = 0; ab < 4; ++ab)
         for (int o = 0; o < F; ++o) {
           const float* src = K + ((size_t)ab * F + o) * l.cin_real;
@@ -785,7 +1021,10 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   L->KC = l.KC;
   L->EPI = l.epi;
   int bn = 0, ns = 0, nacc = 2;
-  if (plan_rows(l, h, w, e ? e->arch.cfg.nclasses : 1, &ns)) {
+  p.dil = l.dil;
+  // dilated 3x3 and 1x1 convolutions (ASPP) exist in the tile kernels only: a tap is a shifted TMA box there
+  const bool generic_only = l.dil != 1 || l.kind == L_CONV1;
+  if (!generic_only && plan_rows(l, h, w, e ? e->arch.cfg.nclasses : 1, &ns)) {
     const bool first = l.KC == 8;  // 8-channel input: boxes of 16 channels, the upper 8 zero-filled by TMA (out of bounds)
     const int kc = first ? 16 : l.KC, cin = first ? 16 : l.cin_pad;
     L->slab = 2;
@@ -815,7 +1054,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
   // weight-streaming halo-slab kernel: Cout = 128 layers whose 3x3 weights exceed shared memory (conv_slabw.cuh);
   // same summation order as the slab / tile kernels, so the choice may depend on the batch size
   const bool slabw_n64 = l.ntotal == 64 && l.cin_pad >= 128 && env_int("SCV_SLABW_N64", 0);  // measured slower (14.4 vs 12.0 ms): off
-  if (env_int("SCV_SLABW", 1) && l.kind == L_CONV3 && l.KC == 64 && (l.ntotal == 128 || slabw_n64) &&
+  if (!generic_only && env_int("SCV_SLABW", 1) && l.kind == L_CONV3 && l.KC == 64 && (l.ntotal == 128 || slabw_n64) &&
       l.cin_pad >= env_int("SCV_SLABW_MIN_CIN", 64) && (l.epi == EPI_STORE || l.epi == EPI_POOL_SKIP) && w % 8 == 0 && h % 16 == 0 &&
       ((long long)B * (h / 16) * (w / 8) >= 4LL * sm_count() || env_int("SCV_SLABW", 1) == 2)) {
     const int wn = l.ntotal;
@@ -840,7 +1079,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     return SCV_OK;
   }
   int pairs = 0;
-  if (plan_slab2(l, B, h, w, &ns, &nacc, &pairs)) {
+  if (!generic_only && plan_slab2(l, B, h, w, &ns, &nacc, &pairs)) {
     L->nacc = nacc;
     L->slab = 6;
     L->BN = kSlab2BN;
@@ -858,7 +1097,7 @@ static int fill_launch(scv_engine* e, const LayerDef& l, const void* in_ptr, int
     SCV_TRY(make_act_tmap(&L->tmA, in_ptr, n_in, h, w, in_pitch, l.KC, 10, 18, 1));
     return SCV_OK;
   }
-  if (plan_slab(l, B, h, w, &bn, &ns, &nacc)) {
+  if (!generic_only && plan_slab(l, B, h, w, &bn, &ns, &nacc)) {
     L->nacc = nacc;
     const int sw = p.ntaps == 9 ? 10 : 8, sh = p.ntaps == 9 ? 18 : 16;
     L->slab = 1;
@@ -954,13 +1193,16 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
   size_t total = 0;
   for (size_t i = 0; i < a.bufs.size(); ++i) {
     const BufDef& b = a.bufs[i];
-    size_t bytes = (size_t)B * (H >> b.level) * (W >> b.level) * b.channels * (b.f32 ? 4 : 2);
+    size_t bytes = (size_t)B * b.mult * (H >> b.level) * (W >> b.level) * b.channels * (b.f32 ? 4 : 2);
     if ((int)i == a.x0_buf || (int)i == a.logits_buf) bytes = 0;  // live in the engine's super-batch tensors
     off[i] = total;
     total += (bytes + 1023) & ~size_t(1023);
   }
   CUDA_TRY(cudaMalloc(&pl->arena, std::max<size_t>(total, 1024)));
   pl->arena_bytes = total;
+  // channel padding of a concat tensor (siamese: 3 F -> a multiple of 64) is read by the next conv against zero weights:
+  // it must hold finite values
+  if (a.cfg.arch == SCV_ARCH_SIAMESE) CUDA_TRY(cudaMemset(pl->arena, 0, std::max<size_t>(total, 1024)));
   pl->buf_ptr.resize(a.bufs.size());
   for (size_t i = 0; i < a.bufs.size(); ++i) pl->buf_ptr[i] = pl->arena + off[i];
   if (!e->d_x0_all || e->tile_cap < B || e->tile_cap_side != H)
@@ -971,8 +1213,13 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
     ConvLaunch Ln;
     const int h = H >> l.level, w = W >> l.level;
     // the layer that reads x0 sees the whole super-batch tensor (tile_cap images) and is offset per launch
-    const int n_in = l.in_buf == a.x0_buf ? e->tile_cap : B;
-    SCV_TRY(fill_launch(e, l, pl->buf_ptr[l.in_buf], a.bufs[l.in_buf].channels, B, h, w, &Ln, n_in));
+    const int n_in = l.in_buf == a.x0_buf ? e->tile_cap : B * l.nmult;
+    // half h of a two-images-per-tile buffer = images [h B, (h + 1) B)
+    auto half_ptr = [&](int buf, int half) {
+      const BufDef& b = a.bufs[buf];
+      return (uint8_t*)pl->buf_ptr[buf] + (size_t)half * B * (H >> b.level) * (W >> b.level) * b.channels * (b.f32 ? 4 : 2);
+    };
+    SCV_TRY(fill_launch(e, l, half_ptr(l.in_buf, l.in_half), a.bufs[l.in_buf].channels, B * l.nmult, h, w, &Ln, n_in));
     ConvParams& p = Ln.p;
     if (l.epi == EPI_HEAD) {
       p.head_w = e->d_head_w;
@@ -980,11 +1227,11 @@ static int get_plan(scv_engine* e, int B, int H, int W, Plan** out) {
       p.ncls = a.cfg.nclasses;
       p.logits = (float*)pl->buf_ptr[l.out_buf];
     } else {
-      p.out = (__nv_bfloat16*)pl->buf_ptr[l.out_buf];
+      p.out = (__nv_bfloat16*)half_ptr(l.out_buf, l.out_half);
       p.out_pitch = a.bufs[l.out_buf].channels;
       p.out_choff = l.out_choff;
       if (l.epi == EPI_POOL_SKIP) {
-        p.pool_out = (__nv_bfloat16*)pl->buf_ptr[l.pool_buf];
+        p.pool_out = (__nv_bfloat16*)half_ptr(l.pool_buf, l.pool_half);
         p.pool_pitch = a.bufs[l.pool_buf].channels;
       }
     }
@@ -1454,7 +1701,7 @@ struct DeviceGuard {
 // =================================================================== C ABI
 extern "C" {
 
-const char* scv_version(void) { return "scv-b200 0.2 (sm_100a, tcgen05/TMEM/TMA)"; }
+const char* scv_version(void) { return "scv-b200 0.3 (sm_100a, tcgen05/TMEM/TMA)"; }
 const char* scv_last_error(void) { return g_err.c_str(); }
 
 int scv_device_count(void) {
@@ -1645,7 +1892,9 @@ static int precheck(scv_engine* e, int dtype, int C) {
   if (!e) return fail(SCV_ERR_INVALID, "engine is NULL");
   if (!e->weights_set) return fail(SCV_ERR_STATE, "predict called before scv_engine_set_weights");
   if (dtype_bytes(dtype) == 0) return fail(SCV_ERR_INVALID, "unknown dtype %d", dtype);
-  if (C != e->arch.cfg.nchannels) return fail(SCV_ERR_INVALID, "input has %d bands, model expects %d", C, e->arch.cfg.nchannels);
+  if (C != input_channels(&e->arch.cfg))
+    return fail(SCV_ERR_INVALID, "input has %d bands, model expects %d%s", C, input_channels(&e->arch.cfg),
+                e->arch.cfg.arch == SCV_ARCH_SIAMESE ? " (the two images stacked along the channel axis)" : "");
   CUDA_TRY(cudaSetDevice(e->device));
   return SCV_OK;
 }

@@ -36,7 +36,7 @@ class UNetModel:
     """
 
     def __init__(self, nclasses, nchannels, filters=None, double_conv=False, head='softmax', threshold=0.5,
-                 bias=None, outputs='both', device=0, max_batch=64, seed=None):
+                 bias=None, outputs='both', device=0, max_batch=64, seed=None, arch=_lib.SCV_ARCH_UNET):
         filters = list(DEFAULT_FILTERS if filters is None else filters)
         if head not in ('softmax', 'sigmoid'):
             raise ValueError("head must be 'softmax' or 'sigmoid'")
@@ -56,6 +56,7 @@ class UNetModel:
         self._cfg.head = _lib.SCV_HEAD_SIGMOID if head == 'sigmoid' else _lib.SCV_HEAD_SOFTMAX
         self._cfg.threshold = self.threshold
         self._cfg.max_batch = self.max_batch
+        self._cfg.arch = int(arch)
         self._lib = _lib.load_library()
         n = self._lib.scv_num_weights(C.byref(self._cfg))
         if n < 0:
@@ -300,7 +301,58 @@ class UNetModel:
         return prob, mask
 
 
+class SiameseUNetModel(UNetModel):
+    """``make_siamese_unet`` (``utils/model_tools.py:638-663``) on the engine: shared single-conv encoder blocks over two
+    images, ``DilatedSpatialPyramidPooling`` (1x1 + 3x3 at dilation 3 / 6 / 12 -> 1x1, ``:533-574``) on both pooled
+    images, decoder over ``concat([encoded_b, encoded_a, up])``, ``Conv2D(1, 1x1, sigmoid)`` + ``int32(p > class_thresh)``.
+
+    ``predict([input_a, input_b])`` like the two-input Keras model; every tiled entry point (``predict_mosaic``,
+    ``predict_patches``, ``prediction_tools.predict_chips`` ...) takes the two rasters stacked along the channel axis,
+    ``np.concatenate([a, b], -1)``.  ``get_weights()`` / ``set_weights()`` use one (kernel, bias, gamma, beta, mean,
+    variance) group per conv-BN unit; ``set_weights(w, order='keras2')`` accepts the list ``tf.keras`` 2 returns, which
+    lists the ASPP layer's trainable weights before its moving statistics."""
+
+    def __init__(self, n_channels, filters=(32, 64, 128), threshold=0.5, bias=None, outputs='both', **engine_kw):
+        super().__init__(1, n_channels, list(filters), double_conv=False, head='sigmoid', threshold=threshold, bias=bias,
+                         outputs=outputs, arch=_lib.SCV_ARCH_SIAMESE, **engine_kw)
+
+    def keras2_permutation(self):
+        """p with ``engine_order[i] = keras2_order[p[i]]`` (see the class docstring)."""
+        n_enc = 6 * len(self.filters)
+        p = list(range(n_enc))
+        for u in range(5):
+            p += [n_enc + 4 * u + j for j in range(4)] + [n_enc + 20 + 2 * u + j for j in range(2)]
+        return p + list(range(n_enc + 30, len(self.weight_shapes)))
+
+    def set_weights(self, weights, order='grouped'):
+        weights = list(weights)
+        if order == 'keras2':
+            if len(weights) != len(self.weight_shapes):
+                raise ValueError(f'expected {len(self.weight_shapes)} weights, got {len(weights)}')
+            weights = [weights[i] for i in self.keras2_permutation()]
+        elif order != 'grouped':
+            raise ValueError("order must be 'grouped' or 'keras2'")
+        super().set_weights(weights)
+
+    def predict(self, x, batch_size=None, verbose=0, steps=None, norm=None):
+        if isinstance(x, (list, tuple)) and len(x) == 2 and all(getattr(v, 'ndim', 0) == 4 for v in x):
+            a, b = (np.asarray(v) for v in x)
+            if a.shape != b.shape or a.shape[-1] != self.nchannels:
+                raise ValueError(f'expected two (N, H, W, {self.nchannels}) inputs, got {a.shape} and {b.shape}')
+            x = np.concatenate([a, b], axis=-1)
+        return super().predict(x, batch_size=batch_size, verbose=verbose, steps=steps, norm=norm)
+
+
 # ---------------------------------------------------------------- reference builders
+def make_siamese_unet(n_channels, filters=[32, 64, 128], factors=[2, 2, 2], bias=None, class_thresh=0.5, **engine_kw):
+    """``utils/model_tools.py:638-663``: two-input change-detection U-Net, outputs ``[probs, classes]``.  ``factors``
+    must all be 2 (``encoder_block`` pool size == ``decoder_block`` up size on this path)."""
+    assert len(filters) == len(factors), 'filters and factors must be same length'
+    if any(int(f) != 2 for f in factors):
+        raise NotImplementedError('only pooling factor 2 is supported')
+    return SiameseUNetModel(n_channels, filters, threshold=class_thresh, bias=bias, **engine_kw)
+
+
 def get_unet_model(nclasses, nchannels, filters=[32, 64, 128, 256, 512], factors=[2, 2, 2, 2, 2], bias=None,
                    dropout=None, head_name: str = '', double_conv=False, **engine_kw):
     """``utils/model_tools.py:394-415``.  ``dropout`` layers are identity at predict time;
