@@ -153,7 +153,7 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def cpu_reference_sample(n_tiles, seed=1, variant='A'):
+def cpu_reference_sample(n_tiles, seed=1, variant='A', arch='unet'):
     """The reference algorithm (generate_chip_indices + per-tile batch-1 predict + crop/stitch) on the
     host cores via the oracle port; returns (MP/s in scene-equivalent pixels, description, cores)."""
     import numpy as np
@@ -162,7 +162,11 @@ def cpu_reference_sample(n_tiles, seed=1, variant='A'):
     from oracle import normalize as onorm
     from oracle import tiling as otile
     from oracle import unet as ounet
-    specs = ounet.weight_specs(variant, BANDS, 1)
+    if arch == 'siamese':
+        from oracle import siamese as osi
+        specs = osi.weight_specs(BANDS // 2)
+    else:
+        specs = ounet.weight_specs(variant, BANDS, 1)
     w = ounet.init_weights(specs, seed=0)
     cols = max(1, n_tiles)
     width = 64 + KERNEL * cols + 192  # exactly `cols` chips in one tile row
@@ -170,7 +174,7 @@ def cpu_reference_sample(n_tiles, seed=1, variant='A'):
     x = onorm.rescale_tensor(arr.astype(np.float32), moments=[(0, 10000)] * BANDS)
     idx = otile.generate_chip_indices(x.shape, BUFF, KERNEL)
     idx = idx[:n_tiles]
-    fn = ounet.make_predict_fn(w, variant=variant)
+    fn = osi.make_predict_fn(w, BANDS // 2) if arch == 'siamese' else ounet.make_predict_fn(w, variant=variant)
     fn(x[None, :384, :384])  # warm-up (thread pool, oneDNN primitives)
     t0 = time.perf_counter()
     otile.predict_chips(x, idx, np.zeros(x.shape[:2]), fn, KERNEL, BUFF)
@@ -223,7 +227,11 @@ def verify_outputs(model, shard, scene_rows, src_row0, W, h_prob, h_mask, d_prob
     use_all_host_threads(threads_share)
     ncols = shard.n_tile_cols
     picks = sorted({int(t) for t in np.linspace(shard.tile_begin, shard.tile_end - 1, n_chips)})
-    fn = ounet.make_predict_fn(model.get_weights(), variant='A')
+    if getattr(model, 'is_siamese', False):
+        from oracle import siamese as osi
+        fn = osi.make_predict_fn(model.get_weights(), BANDS // 2, filters=tuple(model.filters))
+    else:
+        fn = ounet.make_predict_fn(model.get_weights(), variant='A')
     half = BUFF // 2
     max_abs, agree_n, agree_d, dev_equal = 0.0, 0, 0, True
     for t in picks:
@@ -259,6 +267,9 @@ def main():
     ap.add_argument('--gather', action='store_true', help='also time the optional NCCL gather of the shards to rank 0')
     ap.add_argument('--python-api', action='store_true', help='also time prediction_tools.predict_chips (reference signature, '
                                                                'pageable arrays, float64 template) on the full scene (N = 1)')
+    ap.add_argument('--arch', default='unet', choices=['unet', 'siamese'],
+                    help="siamese: make_siamese_unet(3, [32, 64, 128]) on the same scene read as two stacked 3-band dates "
+                         "(SURVEY 8(f) N4; a secondary workload, not the BASELINE metric's configuration)")
     ap.add_argument('--scenes', type=int, default=0, help='BASELINE configs[4]: stream this many scenes through the GPUs')
     ap.add_argument('--stream-mode', default='scenes', choices=['scenes', 'bands'],
                     help='scenes: round-robin whole scenes over the ranks; bands: every scene sharded over all ranks')
@@ -298,7 +309,11 @@ def main():
         return float(t.item())
 
     H = W = args.scene
-    model = model_tools.binary_unet(nchannels=BANDS, device=local_rank, max_batch=args.max_batch, outputs='probs', seed=0)
+    if args.arch == 'siamese':
+        model = model_tools.make_siamese_unet(BANDS // 2, device=local_rank, max_batch=args.max_batch, outputs='probs', seed=0)
+        model.is_siamese = True
+    else:
+        model = model_tools.binary_unet(nchannels=BANDS, device=local_rank, max_batch=args.max_batch, outputs='probs', seed=0)
     model.set_weights(random_weights(model, seed=0))
     spec = processing.rescale_spec(BANDS, moments=[(0, 10000)] * BANDS)
     lib = model._lib
@@ -456,7 +471,7 @@ def main():
         traffic = None  # DRAM bytes of the conv launches of one step: ncu-measured bytes per chip x chips of rank 0
         for name in ('r02_conv_traffic.json', 'r01_k_conv_traffic.json'):
             tp = os.path.join(ROOT, 'profiles', name)
-            if os.path.exists(tp):
+            if os.path.exists(tp) and args.arch == 'unet':
                 with open(tp) as f:
                     traffic = json.load(f)['dram_bytes_per_chip'] * n_my
                 traffic_src = f'profiles/{name} (ncu dram__bytes_read+write, per chip)'
@@ -474,8 +489,12 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': f'synthetic {H}x{W}x{BANDS} uint16 Sentinel-2 scene (BASELINE configs[1]), variant-A U-Net '
-                                   f'(31.1 M params, BN folded), {KERNEL}px kernel + {BUFF}px buffer, {n_chips_total} chips, '
+            'config': {'workload': (f'synthetic {H}x{W}x{BANDS} uint16 scene read as two stacked 3-band dates, siamese U-Net + ASPP '
+                                    f'(make_siamese_unet(3, [32, 64, 128]), 2.4 M params; SECONDARY workload, SURVEY 8(f) N4), '
+                                    if args.arch == 'siamese' else
+                                    f'synthetic {H}x{W}x{BANDS} uint16 Sentinel-2 scene (BASELINE configs[1]), variant-A U-Net '
+                                    f'(31.1 M params, BN folded), ') +
+                                   f'{KERNEL}px kernel + {BUFF}px buffer, {n_chips_total} chips, '
                                    f'{"chip list split evenly" if args.shard == "chips" else "tile rows sharded"} over {world} GPU(s)',
                        'tiles_per_batch': args.max_batch, 'stitched_megapixels': n_chips_total * KERNEL * KERNEL / 1e6,
                        'scene_megapixels': mp_scene, 'chips_rank0': n_my,
@@ -486,13 +505,14 @@ def main():
                                                     'd2h_tail': times_e2e['d2h_tail_ms']}},
             'gpu_launches': int(times['n_launches']) * args.steps,  # rank 0's kernels in the timed device-resident region
             'clocks': clk.summary(),
-            'roofline': {'bound': 'tensor', 'kernel': 'tcgen05 implicit-GEMM conv kernels (all 27 conv/convT layers of the U-Net)',
+            'roofline': {'bound': 'tensor', 'kernel': ('tcgen05 implicit-GEMM conv kernels (all 21 conv/convT launches of the siamese U-Net + ASPP)' if args.arch == 'siamese'
+                                                       else 'tcgen05 implicit-GEMM conv kernels (all 27 conv/convT layers of the U-Net)'),
                          'achieved': tc, 'peak': pk['tc_sustained'], 'unit': 'TFLOP/s',
                          'frac': tc / pk['tc_sustained'] if pk['tc_sustained'] else None,
                          'frac_of_burst_peak': tc / pk['tc_burst'], 'peak_burst': pk['tc_burst'], 'traffic': traffic,
                          'traffic_source': traffic_src if traffic else None,
                          'peak_source': pk['source'],
-                         'how': 'algorithmic FLOPs (67.41 GFLOP per 384x384x6 chip) x chips of rank 0 / CUDA-event time of '
+                         'how': f'algorithmic FLOPs ({flops_tile / 1e9:.2f} GFLOP per 384x384x6 chip) x chips of rank 0 / CUDA-event time of '
                                 'the conv launches of the last timed step; peak = sustained cuBLAS bf16 (kernels timed inside a long step)'},
             'roofline_extract': {'bound': 'hbm', 'achieved': ex_gbs, 'peak': pk['hbm'], 'unit': 'GB/s',
                                  'frac': ex_gbs / pk['hbm'], 'ms': times['extract_ms']},
@@ -511,7 +531,7 @@ def main():
                               for n, m, f in zip(layer_names(model), times['layer_ms'], times['layer_flops'])]
         if world == 1 and not args.no_cpu_baseline:
             use_all_host_threads()
-            v, desc, cores = cpu_reference_sample(args.ref_tiles)
+            v, desc, cores = cpu_reference_sample(args.ref_tiles, arch=args.arch)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -601,6 +621,13 @@ def run_streaming(args, rank, local_rank, world, model, lib, eng, tiling, cn, sh
 def layer_names(model):
     names = []
     L = len(model.filters)
+    if getattr(model, 'is_siamese', False):
+        for i in range(L):
+            names += [f'encoder_{i}/conv0[a]', f'encoder_{i}/conv0[b]']
+        names += ['ASPP/cba', 'ASPP/cba3_3', 'ASPP/cba3_6', 'ASPP/cba3_12', 'ASPP/cba3[a]', 'ASPP/cba3[b]']
+        for i in range(L - 1, -1, -1):
+            names += [f'decoder_{i}/up', f'decoder_{i}/conv0', f'decoder_{i}/conv1']
+        return names
     nconv = 2 if model.double_conv else 1
     for i in range(L):
         names += [f'encoder_{i}/conv{j}' for j in range(nconv)]
