@@ -141,7 +141,8 @@ static int pad_channels(int c) {
   if (c <= 32) return 32;
   return (c + 63) / 64 * 64;
 }
-static int kc_for(int cpad) { return cpad <= 8 ? 8 : (cpad <= 16 ? 16 : (cpad <= 32 ? 32 : 64)); }
+// channel chunk of a layer's K loop; a 96-channel tensor (the siamese decoder entry at 32 filters) runs as three chunks of 32
+static int kc_for(int cpad) { return cpad <= 8 ? 8 : (cpad <= 16 ? 16 : ((cpad <= 32 || cpad % 64) ? 32 : 64)); }
 // K extent of a layer's weight matrix: taps * Cin_pad, except the 8-channel first layer (9 taps -> ten 8-wide slices)
 static size_t k_total(int kc, int ntaps, int cin_pad) { return kc == 8 ? 80 : (size_t)ntaps * cin_pad; }
 static int bn_for(int ntotal) {
@@ -509,7 +510,11 @@ static int build_arch_siamese(const scv_config* c, Arch* a) {
   a->x0_buf = add_buf(0, a->c0pad, false, "x0", 1);
   std::vector<int> cat(L), pooled(L), t(L), d2(L, -1);
   for (int i = 0; i < L; ++i) {
-    cat[i] = add_buf(i, pad_channels(3 * c->filters[i]), false, "cat" + std::to_string(i), 1);
+    // 3 F channels; F = 32 gives 96 = three 32-channel chunks (padding it to 128 cost the 384-pixel decoder conv its
+    // row-kernel form: 30.9 ms in the N = 32 slab kernel against 13.4 ms; the 192-byte pixel pitch costs the two
+    // encoder epilogues and the transposed conv that write into it 2 ms each, net -13 ms per scene)
+    cat[i] = add_buf(i, 3 * c->filters[i] % 32 == 0 ? 3 * c->filters[i] : pad_channels(3 * c->filters[i]), false,
+                     "cat" + std::to_string(i), 1);
     pooled[i] = add_buf(i + 1, c->filters[i], false, "pool" + std::to_string(i), 2);
     t[i] = add_buf(i, c->filters[i], false, "t" + std::to_string(i), 1);
     if (i > 0) d2[i] = add_buf(i, c->filters[i], false, "dec" + std::to_string(i), 1);
