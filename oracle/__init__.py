@@ -8,6 +8,8 @@ predict path (mjevans26/Satellite_ComputerVision):
 * ``oracle.normalize`` -- ``utils/processing.py:225-322``, ``utils/pc_tools.py:90-107``
 * ``oracle.unet``      -- ``utils/model_tools.py:174-454`` and
   ``notebooks/UNET_G4G_2019_solar.ipynb:1162-1213``
+* ``oracle.siamese``   -- ``utils/model_tools.py:533-663`` (siamese U-Net with the atrous pyramid; float arithmetic
+  unpinned like the U-Net's, cross-checked against ``oracle.siamese.naive_*`` in ``tests/test_siamese.py``)
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import it, and only as the checker / the timed
