@@ -68,12 +68,48 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// try_wait with a suspend-time hint: the thread stays descheduled until the phase completes or `hint_ns` have passed,
+// instead of returning after the (much shorter) system default and being re-issued.  Measured motivation (ncu source
+// page of the fused encoder pair, profiles/r02_new_kernels_full.md): with the default limit a waiting warp came back
+// ~40 times per wait, and those spin iterations (TRYWAIT + branch + bookkeeping, ~10 instructions each) were 43 % of
+// all warp instructions executed by that kernel.  Measured A/B on one box (tools/r02_exp35.sh, whole step): 114.67 /
+// 114.22 ms with the hint against 114.69 / 114.65 ms without -- the spinning warps were only filling issue slots nobody
+// else wanted; kept because it is never slower and retires 40 % fewer instructions.  -DSCV_WAIT_HINT_NS=0: plain spin.
+#ifndef SCV_WAIT_HINT_NS
+#define SCV_WAIT_HINT_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(SCV_WAIT_HINT_NS))
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: returns false (and latches *abort_flag) when the barrier has not
 // flipped within `budget_ns`, or when another role already aborted.  A stalled
 // pipeline therefore ends in a clean kernel exit (TMEM freed) plus an error code
 // instead of a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
                                           uint64_t budget_ns) {
+#if SCV_WAIT_HINT_NS > 0
+  if (mbar_try_wait_hint(bar, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  while (true) {  // one iteration per expired hint (tens of microseconds): check the watchdog every time
+    if (mbar_try_wait_hint(bar, parity)) return true;
+    if (*abort_flag) return false;
+    if (globaltimer_ns() - t0 > budget_ns) {
+      *abort_flag = 1;
+      return false;
+    }
+  }
+#else
   if (mbar_try_wait(bar, parity)) return true;
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
@@ -87,6 +123,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
       }
     }
   }
+#endif
 }
 
 // ---------------------------------------------------------------------- TMA
