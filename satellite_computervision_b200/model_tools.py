@@ -334,6 +334,22 @@ class SiameseUNetModel(UNetModel):
             raise ValueError("order must be 'grouped' or 'keras2'")
         super().set_weights(weights)
 
+    def load_weights(self, path, by_name=False, skip_mismatch=False, order='grouped'):
+        """``.npz`` written as ``np.savez(path, *model.get_weights())`` (``order='keras2'`` for a list taken from the
+        reference's ``tf.keras`` model).  Keras HDF5 files of this architecture are not mapped: the reader's layer
+        matching (``keras_h5.py``) covers the U-Net families only."""
+        if not str(path).endswith('.npz'):
+            raise NotImplementedError('SiameseUNetModel.load_weights: only .npz weight lists are supported '
+                                      '(np.savez(path, *keras_model.get_weights()), order="keras2")')
+        with np.load(path) as z:
+            keys = sorted(z.files, key=lambda k: int(k.split('_')[1]) if k.startswith('arr_') else 0)
+            self.set_weights([z[k] for k in keys], order=order)
+
+    def save_weights(self, path):
+        if not str(path).endswith('.npz'):
+            raise NotImplementedError('SiameseUNetModel.save_weights: .npz only')
+        np.savez(path, *self._weights)
+
     def predict(self, x, batch_size=None, verbose=0, steps=None, norm=None):
         if isinstance(x, (list, tuple)) and len(x) == 2 and all(getattr(v, 'ndim', 0) == 4 for v in x):
             a, b = (np.asarray(v) for v in x)

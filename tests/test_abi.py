@@ -29,6 +29,11 @@ def test_exports_every_declared_symbol(lib):
     assert b'sm_100a' in lib.scv_version()
 
 
+def test_version_string():
+    lib = _lib.load_library()
+    assert b'0.3' in lib.scv_version() and b'sm_100a' in lib.scv_version()
+
+
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Config) == 4 * (5 + 8 + 4)  # ... + arch (0.3)
     assert C.sizeof(_lib.Tensor) == 8 + 8 + 32

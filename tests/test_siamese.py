@@ -76,5 +76,29 @@ def test_engine_weight_list_equals_oracle():
         assert all(np.array_equal(x, y) for x, y in zip(m.get_weights(), m2.get_weights()))
     with pytest.raises(Exception):
         model_tools.make_siamese_unet(9)  # 2 x 9 bands exceed the extract kernel's band limit
+    with pytest.raises(ValueError):
+        m.set_weights(w[:-1])
+    with pytest.raises(NotImplementedError):
+        m.load_weights('weights.h5')
     with pytest.raises(NotImplementedError):
         model_tools.make_siamese_unet(3, [32, 64], [2, 4])
+
+
+def test_npz_round_trip(tmp_path):
+    from satellite_computervision_b200 import model_tools
+    m = model_tools.make_siamese_unet(3, seed=3)
+    path = str(tmp_path / 'siamese.npz')
+    m.save_weights(path)
+    m2 = model_tools.make_siamese_unet(3, seed=4)
+    assert not all(np.array_equal(x, y) for x, y in zip(m.get_weights(), m2.get_weights()))
+    m2.load_weights(path)
+    assert all(np.array_equal(x, y) for x, y in zip(m.get_weights(), m2.get_weights()))
+    # a list in tf.keras 2 order goes through the permutation
+    w = m.get_weights()
+    keras2 = [None] * len(w)
+    for i, src in enumerate(m.keras2_permutation()):
+        keras2[src] = w[i]
+    np.savez(str(tmp_path / 'k2.npz'), *keras2)
+    m3 = model_tools.make_siamese_unet(3, seed=5)
+    m3.load_weights(str(tmp_path / 'k2.npz'), order='keras2')
+    assert all(np.array_equal(x, y) for x, y in zip(w, m3.get_weights()))
