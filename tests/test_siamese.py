@@ -102,3 +102,13 @@ def test_npz_round_trip(tmp_path):
     m3 = model_tools.make_siamese_unet(3, seed=5)
     m3.load_weights(str(tmp_path / 'k2.npz'), order='keras2')
     assert all(np.array_equal(x, y) for x, y in zip(w, m3.get_weights()))
+
+
+def test_real_keras_siamese_matches_oracle_when_tensorflow_is_present():
+    """The siamese oracle restates Keras like the U-Net oracle does; when TensorFlow imports, build the reference's own
+    layer classes with tf.keras and pin both the arithmetic and the get_weights() order of the composite ASPP layer."""
+    tf = pytest.importorskip('tensorflow')
+    from oracle import keras_probe
+    err, order = keras_probe.compare_siamese(tf)
+    print('siamese oracle vs tf.keras: max|dp|', err, 'weight order', order)
+    assert err <= 1e-4
